@@ -1,0 +1,159 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE -- see oracle/nno_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The product package nnnoiseless_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libnno_oracle.so")
+FRAME_SIZE = 480
+NB_BANDS = 22
+NB_FEATURES = 42
+
+
+def build(force=False):
+    """Compile oracle/nno_oracle.c with gcc (see oracle/Makefile)."""
+    src = [os.path.join(_HERE, f) for f in ("nno_oracle.c", "nno_oracle.h", "Makefile")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+class Taps(C.Structure):
+    _fields_ = [
+        ("pitch", C.c_int32),
+        ("silence", C.c_int32),
+        ("vad", C.c_float),
+        ("pitch_gain", C.c_float),
+        ("features", C.c_float * NB_FEATURES),
+        ("gains", C.c_float * NB_BANDS),
+        ("ex", C.c_float * NB_BANDS),
+        ("ep", C.c_float * NB_BANDS),
+        ("exp", C.c_float * NB_BANDS),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.nno_model_from_bytes.restype = C.c_void_p
+        L.nno_model_from_bytes.argtypes = [C.c_char_p, C.c_size_t]
+        L.nno_model_free.argtypes = [C.c_void_p]
+        L.nno_model_describe.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        L.nno_state_new.restype = C.c_void_p
+        L.nno_state_new.argtypes = [C.c_void_p]
+        L.nno_state_free.argtypes = [C.c_void_p]
+        L.nno_process_frame.restype = C.c_float
+        L.nno_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nno_get_taps.argtypes = [C.c_void_p, C.POINTER(Taps)]
+        L.nno_rfft960.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nno_irfft960.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nno_pitch_only.restype = C.c_int32
+        L.nno_pitch_only.argtypes = [C.c_void_p, C.c_void_p]
+        L.nno_tansig.restype = C.c_float
+        L.nno_tansig.argtypes = [C.c_float]
+        L.nno_sigmoid.restype = C.c_float
+        L.nno_sigmoid.argtypes = [C.c_float]
+        L.nno_run_batch.restype = C.c_double
+        L.nno_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Model:
+    def __init__(self, data: bytes):
+        self._h = lib().nno_model_from_bytes(data, len(data))
+        if not self._h:
+            raise ValueError("oracle: model bytes rejected")
+
+    def describe(self):
+        out = (C.c_int32 * 18)()
+        lib().nno_model_describe(self._h, out)
+        return [tuple(out[3 * i:3 * i + 3]) for i in range(6)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().nno_model_free(self._h)
+            self._h = None
+
+
+def model_accepts(data: bytes) -> bool:
+    h = lib().nno_model_from_bytes(data, len(data))
+    if h:
+        lib().nno_model_free(h)
+    return bool(h)
+
+
+class State:
+    def __init__(self, model: Model):
+        self.model = model
+        self._h = lib().nno_state_new(model._h)
+
+    def process_frame(self, frame: np.ndarray):
+        frame = np.ascontiguousarray(frame, dtype=np.float32)
+        assert frame.shape == (FRAME_SIZE,)
+        out = np.empty(FRAME_SIZE, np.float32)
+        vad = lib().nno_process_frame(self._h, _ptr(out), _ptr(frame))
+        return out, float(vad)
+
+    def taps(self) -> Taps:
+        t = Taps()
+        lib().nno_get_taps(self._h, C.byref(t))
+        return t
+
+    def pitch_only(self, buf1728):
+        buf = np.ascontiguousarray(buf1728, dtype=np.float32)
+        assert buf.shape == (1728,)
+        return int(lib().nno_pitch_only(self._h, _ptr(buf)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().nno_state_free(self._h)
+            self._h = None
+
+
+def rfft960(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    re = np.empty(481, np.float32)
+    im = np.empty(481, np.float32)
+    lib().nno_rfft960(_ptr(x), _ptr(re), _ptr(im))
+    return re + 1j * im
+
+
+def irfft960(X):
+    re = np.ascontiguousarray(X.real, dtype=np.float32)
+    im = np.ascontiguousarray(X.imag, dtype=np.float32)
+    out = np.empty(960, np.float32)
+    lib().nno_irfft960(_ptr(re), _ptr(im), _ptr(out))
+    return out
+
+
+def run_batch(model: Model, x: np.ndarray, n_threads=0, want_out=True, want_taps=True):
+    """x: [B][T][480] float32.  Returns dict(out, vad, pitch, seconds, threads)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    B, T, F = x.shape
+    assert F == FRAME_SIZE
+    out = np.empty_like(x) if want_out else None
+    vad = np.empty((B, T), np.float32) if want_taps else None
+    pitch = np.empty((B, T), np.int32) if want_taps else None
+    used = C.c_int(0)
+    secs = lib().nno_run_batch(model._h, _ptr(x), _ptr(out), _ptr(vad), _ptr(pitch), B, T, n_threads, C.byref(used))
+    return dict(out=out, vad=vad, pitch=pitch, seconds=float(secs), threads=int(used.value))

@@ -1,0 +1,86 @@
+/*
+ * nno_oracle.h -- CPU ORACLE for the nnnoiseless per-frame denoise path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference
+ * algorithm (jneem/nnnoiseless @ 7b47c9b, DenoiseState::process_frame) used as
+ * the checker for the CUDA path and as the timed CPU baseline.  Nothing in the
+ * product package (nnnoiseless_b200/) may include, link or call it; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs do.
+ *
+ * Pinning: the oracle reproduces the reference's only golden vector
+ * (test_data/testing.raw -> test_data/reference_output.raw, metric of
+ * src/lib.rs:184-194) -- see tests/test_oracle_golden.py.  Intermediates
+ * (pitch index, VAD, features, gains) are NOT pinned by any reference test
+ * (the reference has none); they are pinned transitively through that vector.
+ * The Rust crate itself cannot be built here (no rustc/cargo), so the FFT
+ * (easyfft 0.4.2 -> realfft 3.5.0 -> rustfft 6.4.1, not vendored) is restated
+ * from its published semantics: unnormalised forward e^{-i}, unnormalised
+ * inverse, bin 0 = DC, bin 480 = Nyquist.
+ */
+#ifndef NNO_ORACLE_H
+#define NNO_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNO_FRAME_SIZE 480
+#define NNO_NB_BANDS 22
+#define NNO_NB_FEATURES 42
+
+typedef struct nno_model nno_model;
+typedef struct nno_state nno_state;
+
+/* Per-frame intermediates of the most recent nno_process_frame call. */
+typedef struct {
+    int32_t pitch;     /* pitch period returned by PitchFinder::process, in [60, 768] */
+    int32_t silence;   /* 1 if compute_frame_features returned true */
+    float vad;         /* return value of process_frame */
+    float pitch_gain;  /* PitchFinder last_gain */
+    float features[NNO_NB_FEATURES];
+    float gains[NNO_NB_BANDS]; /* g after the 0.6*lastg floor (== lastg); zeros on silent frames */
+    float ex[NNO_NB_BANDS];
+    float ep[NNO_NB_BANDS];
+    float exp[NNO_NB_BANDS];
+} nno_taps;
+
+/* RnnModel::from_bytes (src/rnn.rs:75,116-232).  NULL on any format violation. */
+nno_model *nno_model_from_bytes(const uint8_t *bytes, size_t len);
+void nno_model_free(nno_model *m);
+/* layer geometry, for tests: out[0..18) = {ni, nn, act} x 6 layers in file order */
+void nno_model_describe(const nno_model *m, int32_t out[18]);
+
+/* DenoiseState::with_model (src/denoise.rs:72-82): borrows the model. */
+nno_state *nno_state_new(const nno_model *m);
+void nno_state_free(nno_state *s);
+/* DenoiseState::process_frame (src/denoise.rs:95-116).  out may alias in. */
+float nno_process_frame(nno_state *s, float *out, const float *in);
+void nno_get_taps(const nno_state *s, nno_taps *taps);
+
+/* Exposed pieces for unit tests. */
+void nno_rfft960(const float *in960, float *out_re481, float *out_im481);
+void nno_irfft960(const float *re481, const float *im481, float *out960);
+int32_t nno_pitch_only(nno_state *s, const float *buf1728);
+float nno_tansig(float x);
+float nno_sigmoid(float x);
+
+/*
+ * Batched driver used as the timed CPU baseline: n_streams independent states,
+ * each advanced n_frames frames.  in/out: [n_streams][n_frames][480] floats
+ * (out may be NULL to discard).  vad (may be NULL): [n_streams][n_frames].
+ * pitch (may be NULL): [n_streams][n_frames].  Streams are distributed over
+ * n_threads OpenMP threads (<=0: all).  Returns elapsed seconds of the
+ * processing loop (state construction excluded) and the thread count used in
+ * *threads_used.
+ */
+double nno_run_batch(const nno_model *m, const float *in, float *out, float *vad, int32_t *pitch,
+                     int n_streams, int n_frames, int n_threads, int *threads_used);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

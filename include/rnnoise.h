@@ -1,0 +1,120 @@
+/* SPDX-License-Identifier: BSD-3-Clause */
+/*
+ * rnnoise.h -- C ABI of nnnoiseless-b200.
+ *
+ * Part 1 is the drop-in boundary: the eight rnnoise_* functions the reference exports from
+ * src/capi.rs (jneem/nnnoiseless @ 7b47c9b; header generated there by cbindgen per cbindgen.toml:
+ * guard RNNOISE_H, <stdio.h>, C++ compatible).  Same names, argument meaning, ownership and error
+ * behaviour -- test_data/rnnoise_demo.c compiles against this header unchanged.
+ *
+ * Part 2 is additive: a batched entry point (one call advances N independent streams), because a
+ * one-frame-one-stream call cannot feed a GPU.  The legacy functions are N = 1 wrappers over the
+ * same kernels.
+ *
+ * All computation runs in hand-written sm_100a CUDA kernels; there is no CPU fallback: without a
+ * usable CUDA device rnnoise_create / rnnoise_batch_create return NULL and rnnoise_last_error()
+ * says why.
+ */
+#ifndef RNNOISE_H
+#define RNNOISE_H
+
+#include <stdio.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct DenoiseState DenoiseState; /* src/capi.rs:9  */
+typedef struct RNNModel RNNModel;         /* src/capi.rs:11 */
+
+/* ------------------------------------------------------------------ Part 1: reference ABI ---- */
+
+/* Number of samples processed per call: 480.  Replaces src/capi.rs:17-19. */
+int rnnoise_get_frame_size(void);
+
+/* Size of DenoiseState in bytes (for rnnoise_init on caller memory).  Replaces src/capi.rs:25-27. */
+int rnnoise_get_size(void);
+
+/* Initialise a caller-allocated DenoiseState of rnnoise_get_size() bytes; model NULL = built-in.
+ * Returns 0 on success (the reference always returns 0; we return -1 if no CUDA device/stream could
+ * be set up -- see rnnoise_last_error).  Replaces src/capi.rs:29-43. */
+int rnnoise_init(DenoiseState *st, RNNModel *model);
+
+/* Allocate + initialise a state; model NULL = built-in weights.  A non-NULL model is BORROWED and
+ * must outlive the state (Cow::Borrowed, src/capi.rs:53).  Replaces src/capi.rs:49-57. */
+DenoiseState *rnnoise_create(RNNModel *model);
+
+/* Free a state returned by rnnoise_create.  Replaces src/capi.rs:63-65. */
+void rnnoise_destroy(DenoiseState *st);
+
+/* Denoise one frame of 480 samples (floats in the int16 range); out may alias in.  Returns the
+ * voice-activity probability.  A NULL state aborts, as the reference's `expect` does.
+ * Replaces src/capi.rs:75-85. */
+float rnnoise_process_frame(DenoiseState *st, float *out, float *in);
+
+/* Load a model in the nnnoiseless binary format.  Takes over the FILE: it is read to EOF and
+ * fclose()d.  NULL on read error or malformed model.  Replaces src/capi.rs:89-105. */
+RNNModel *rnnoise_model_from_file(FILE *file);
+
+/* Free a model returned by rnnoise_model_from_file / _from_bytes.  Replaces src/capi.rs:111-113. */
+void rnnoise_model_free(RNNModel *model);
+
+/* ------------------------------------------------------------------ Part 2: additive ---------- */
+
+/* RnnModel::from_bytes (src/rnn.rs:75): parse a model from memory (bytes are copied).  NULL if the
+ * bytes are not a valid model (same validation as src/rnn.rs:189-222). */
+RNNModel *rnnoise_model_from_bytes(const unsigned char *bytes, size_t len);
+
+/* RNNoise text format ("rnnoise-nu model file version 1", e.g. test_data/sh.rnnn) -> model, i.e.
+ * train/convert_rnnoise.py:18-29 followed by from_bytes. */
+RNNModel *rnnoise_model_from_text(const char *text, size_t len);
+
+/* Copy the model's binary image (the exact bytes from_bytes accepted) into buf; returns its size.
+ * With buf NULL only the size is returned.  Used to broadcast a model between ranks. */
+size_t rnnoise_model_bytes(const RNNModel *model, unsigned char *buf, size_t cap);
+
+typedef struct RNNoiseBatch RNNoiseBatch;
+
+/* A batch of n_streams independent DenoiseStates living on CUDA device `device` (-1: current).
+ * model NULL = built-in; the model's weights are copied to the device (the model may be freed). */
+RNNoiseBatch *rnnoise_batch_create(const RNNModel *model, int n_streams, int device);
+void rnnoise_batch_destroy(RNNoiseBatch *b);
+int rnnoise_batch_streams(const RNNoiseBatch *b);
+/* Zero every stream's state (== freshly created). */
+int rnnoise_batch_reset(RNNoiseBatch *b);
+
+/* Advance every stream by n_frames frames.  DEVICE pointers.
+ *   in, out : sample (s, t, i) at  ptr[s * stream_stride + t * frame_stride + i],  i < 480
+ *             (floats; strides in floats; out may alias in)
+ *   vad     : [n_frames][n_streams] voice-activity probabilities, or NULL
+ *   cuda_stream : a cudaStream_t (NULL = the batch's own stream); the call is asynchronous
+ *             with respect to the host when a stream is given.
+ * Returns 0, or a negative error code (rnnoise_last_error() has the text). */
+int rnnoise_batch_process_device(RNNoiseBatch *b, float *out, const float *in, float *vad, int n_frames,
+                                 long stream_stride, long frame_stride, void *cuda_stream);
+
+/* Same through HOST buffers: copies in -> device, runs, copies out/vad back, synchronises.
+ * Layout [n_frames][n_streams][480] (frame-major), vad [n_frames][n_streams]. */
+int rnnoise_batch_process_host(RNNoiseBatch *b, float *out, const float *in, float *vad, int n_frames);
+
+/* PCM front-end (what both reference front-ends do around the path: src/nnnoiseless.rs:147-177,
+ * test_data/rnnoise_demo.c:51-55): int16 samples in, process, round-to-nearest + clamp to int16
+ * out.  HOST buffers, layout [n_frames][n_streams][480]. */
+int rnnoise_batch_process_pcm16_host(RNNoiseBatch *b, short *out, const short *in, float *vad, int n_frames);
+
+/* Debug taps of the most recent frame (DEVICE -> host copies; any pointer may be NULL):
+ *   pitch [n_streams] int, silence [n_streams] int, features [n_streams][42], gains [n_streams][22]
+ *   (gains after the 0.6*lastg floor). */
+int rnnoise_batch_get_taps(RNNoiseBatch *b, int *pitch, int *silence, float *features, float *gains);
+
+/* Number of kernel launches issued by this library since load (bench evidence). */
+unsigned long long rnnoise_kernel_launches(void);
+
+/* Text of the most recent error on this thread ("" if none). */
+const char *rnnoise_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNNOISE_H */

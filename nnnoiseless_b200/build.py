@@ -1,0 +1,73 @@
+"""Builds libnnnoiseless_b200.so (hand-written sm_100a CUDA kernels + the C ABI of include/rnnoise.h).
+
+In-tree build with nvcc (cross-compiles without a GPU):
+    python -m nnnoiseless_b200.build [--force]
+The .so is git-ignored but travels to the GPU box with the tree.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libnnnoiseless_b200.so")
+WEIGHTS = os.path.join(HERE, "data", "weights.rnn")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+# (source, extra flags).  exact.cu is the order-exact pitch path: no FMA contraction.
+UNITS = [
+    ("exact.cu", ["-fmad=false"]),
+    ("spectral.cu", []),
+    ("rnn.cu", []),
+    ("host.cu", []),
+]
+HEADERS = ["common.cuh", "model.hpp", os.path.join("..", "..", "include", "rnnoise.h")]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    logs = []
+    for src, extra in UNITS:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src + ".o")
+        objs.append(o)
+        if force or _newer(o, [s] + hdrs):
+            cmd = [NVCC] + ARCH + COMMON + extra + ["-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            logs.append(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed on " + src)
+            if verbose:
+                sys.stderr.write(r.stderr)
+    s = os.path.join(CSRC, "model.cpp")
+    o = os.path.join(OBJ, "model.cpp.o")
+    objs.append(o)
+    if force or _newer(o, [s, WEIGHTS] + hdrs):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", '-DNNB_WEIGHTS_PATH="%s"' % WEIGHTS, "-c", s, "-o", o]
+        subprocess.run(cmd, check=True)
+    if force or _newer(LIB, objs):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
+        subprocess.run(cmd, check=True)
+    with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
+        f.write("".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

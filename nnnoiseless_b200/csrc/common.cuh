@@ -1,0 +1,102 @@
+// common.cuh -- shared constants, device tables and per-batch state layout for the
+// B200 (sm_100a) implementation of nnnoiseless' DenoiseState::process_frame.
+//
+// Reference constants: src/lib.rs:36-58 (jneem/nnnoiseless @ 7b47c9b).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nnb {
+
+constexpr int FRAME_SIZE = 480;
+constexpr int WINDOW_SIZE = 960;
+constexpr int FREQ_SIZE = 481;
+constexpr int PITCH_MIN_PERIOD = 60;
+constexpr int PITCH_MAX_PERIOD = 768;
+constexpr int PITCH_FRAME_SIZE = 960;
+constexpr int PITCH_BUF_SIZE = PITCH_MAX_PERIOD + PITCH_FRAME_SIZE;  // 1728
+constexpr int NB_BANDS = 22;
+constexpr int CEPS_MEM = 8;
+constexpr int NB_DELTA_CEPS = 6;
+constexpr int NB_FEATURES = 42;
+constexpr int MAX_NEURONS = 128;
+constexpr int NB_BINS_BANDED = 400;  // bins covered by the 21 band segments (EBAND_5MS[21] << 2)
+
+// History ring: 4 slots of one frame each.  After frame f is written to slot f % 4 the most
+// recent PITCH_BUF_SIZE samples (the reference's input_mem, src/features.rs:21,97-104) are the
+// ring positions (base + i) mod HIST_CAP, i = 0..1727, base = (slot*480 + 672) mod 1920.
+constexpr int HIST_SLOTS = 4;
+constexpr int HIST_CAP = HIST_SLOTS * FRAME_SIZE;  // 1920
+
+__host__ __device__ inline int hist_base(int slot) { return (slot * FRAME_SIZE + (HIST_CAP - (PITCH_BUF_SIZE - FRAME_SIZE))) % HIST_CAP; }
+
+// Read-only tables shared by all kernels (built on the host in f64 exactly as src/lib.rs:107-127).
+struct DeviceTables {
+    float window[WINDOW_SIZE];
+    float dct[NB_BANDS * NB_BANDS];  // [i][j] = cos((i+.5) j pi/22), column 0 scaled by sqrt(.5)
+    float wnorm;                     // 1 / sum(window^2)
+    float tansig[201 + 3];           // src/util.rs:3-27 (+pad)
+    float2 tw480[480];               // exp(-2 pi i k/480)
+    float2 tw960[FREQ_SIZE + 3];     // exp(-2 pi i k/960), k = 0..480
+    // band interpolation tables for bins 0..399 (src/lib.rs:65-97): bin idx belongs to band
+    // segment band_of[idx] with frac band_frac[idx] = j / band_size (f32 division)
+    float band_frac[NB_BINS_BANDED];
+    int32_t band_of[NB_BINS_BANDED];
+    int32_t band_start[NB_BANDS];  // EBAND_5MS[i] << 2
+};
+
+// One dense or GRU layer as laid out on the device (f32-expanded int8 weights).
+//   dense: w[ni][nn], bias[nn]
+//   gru  : wzr[(ni+nn)][2nn]  rows 0..ni-1 = input weights (gates z|r), rows ni.. = recurrent
+//          wh [(ni+nn)][nn]   same for the candidate gate
+//          bias[3nn] (z|r|h)
+struct DeviceLayer {
+    int ni, nn, act;
+    const float* w;     // dense: [ni][nn]; gru: wzr
+    const float* wh;    // gru only
+    const float* bias;  // f32(int8)
+};
+
+struct DeviceModel {
+    DeviceLayer input_dense, vad_gru, noise_gru, denoise_gru, denoise_output, vad_output;
+    int state_size;  // vad.nn + noise.nn + denoise.nn
+};
+
+// Per-batch persistent state + per-step intermediates, all [n_streams][...] row-major in HBM.
+struct BatchBuffers {
+    int n_streams;
+    // persistent (src/features.rs:18-46, src/pitch.rs:4-17, src/rnn.rs:65-70, src/denoise.rs:39)
+    float* hist;         // [B][HIST_CAP] ring of high-passed input
+    float* hp_mem;       // [B][2]
+    float* synth_mem;    // [B][480]
+    float* ceps_mem;     // [B][8][22]
+    int32_t* ceps_id;    // [B]
+    int32_t* last_period;  // [B]
+    float* last_gain;    // [B]
+    float* gru_state;    // [B][state_size]  (vad | noise | denoise)
+    float* lastg;        // [B][22]
+    // per-step intermediates
+    float2* X;           // [B][481]
+    float2* P;           // [B][400]
+    float* ex;           // [B][22]
+    float* ep;           // [B][22]
+    float* exp;          // [B][22]
+    float* features;     // [B][42]
+    int32_t* silence;    // [B]
+    int32_t* pitch;      // [B]
+    float* gains;        // [B][22]  raw RNN gains
+    float* vad;          // [B]
+};
+
+// ---- launchers (one per translation unit) ------------------------------------------------------
+// exact.cu (compiled with -fmad=false: bit-exact pitch path)
+cudaError_t launch_hp_filter(const BatchBuffers& b, const float* in, long stream_stride, int slot, cudaStream_t st);
+cudaError_t launch_pitch(const BatchBuffers& b, int slot, cudaStream_t st);
+// spectral.cu
+cudaError_t launch_analysis(const BatchBuffers& b, const DeviceTables* tab, int slot, cudaStream_t st);
+cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, float* out, long stream_stride, float* vad_out,
+                             cudaStream_t st);
+// rnn.cu
+cudaError_t launch_rnn(const BatchBuffers& b, const DeviceModel& m, const DeviceTables* tab, cudaStream_t st);
+
+}  // namespace nnb

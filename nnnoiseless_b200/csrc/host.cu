@@ -1,0 +1,511 @@
+// host.cu -- host side of the C ABI declared in include/rnnoise.h: table construction, model upload,
+// the batch handle that owns the per-stream device state, and the per-frame launch sequence
+//   hp_filter -> pitch -> analysis -> rnn -> synthesis
+// which together are DenoiseState::process_frame (src/denoise.rs:95-116) for n_streams streams.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rnnoise.h"
+#include "common.cuh"
+#include "model.hpp"
+
+using namespace nnb;
+
+struct RNNModel {
+    HostModel m;
+};
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(const std::string& what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) {
+        g_err += ": ";
+        g_err += cudaGetErrorString(e);
+    }
+    return -1;
+}
+
+#define CK(call)                                         \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return fail(#call, e__); \
+    } while (0)
+
+// ---- tables (src/lib.rs:99-136, src/util.rs:3-27) -------------------------------------------------
+const float kTansig[201] = {
+    0.000000f, 0.039979f, 0.079830f, 0.119427f, 0.158649f, 0.197375f, 0.235496f, 0.272905f, 0.309507f, 0.345214f, 0.379949f,
+    0.413644f, 0.446244f, 0.477700f, 0.507977f, 0.537050f, 0.564900f, 0.591519f, 0.616909f, 0.641077f, 0.664037f, 0.685809f,
+    0.706419f, 0.725897f, 0.744277f, 0.761594f, 0.777888f, 0.793199f, 0.807569f, 0.821040f, 0.833655f, 0.845456f, 0.856485f,
+    0.866784f, 0.876393f, 0.885352f, 0.893698f, 0.901468f, 0.908698f, 0.915420f, 0.921669f, 0.927473f, 0.932862f, 0.937863f,
+    0.942503f, 0.946806f, 0.950795f, 0.954492f, 0.957917f, 0.961090f, 0.964028f, 0.966747f, 0.969265f, 0.971594f, 0.973749f,
+    0.975743f, 0.977587f, 0.979293f, 0.980869f, 0.982327f, 0.983675f, 0.984921f, 0.986072f, 0.987136f, 0.988119f, 0.989027f,
+    0.989867f, 0.990642f, 0.991359f, 0.992020f, 0.992631f, 0.993196f, 0.993718f, 0.994199f, 0.994644f, 0.995055f, 0.995434f,
+    0.995784f, 0.996108f, 0.996407f, 0.996682f, 0.996937f, 0.997172f, 0.997389f, 0.997590f, 0.997775f, 0.997946f, 0.998104f,
+    0.998249f, 0.998384f, 0.998508f, 0.998623f, 0.998728f, 0.998826f, 0.998916f, 0.999000f, 0.999076f, 0.999147f, 0.999213f,
+    0.999273f, 0.999329f, 0.999381f, 0.999428f, 0.999472f, 0.999513f, 0.999550f, 0.999585f, 0.999617f, 0.999646f, 0.999673f,
+    0.999699f, 0.999722f, 0.999743f, 0.999763f, 0.999781f, 0.999798f, 0.999813f, 0.999828f, 0.999841f, 0.999853f, 0.999865f,
+    0.999875f, 0.999885f, 0.999893f, 0.999902f, 0.999909f, 0.999916f, 0.999923f, 0.999929f, 0.999934f, 0.999939f, 0.999944f,
+    0.999948f, 0.999952f, 0.999956f, 0.999959f, 0.999962f, 0.999965f, 0.999968f, 0.999970f, 0.999973f, 0.999975f, 0.999977f,
+    0.999978f, 0.999980f, 0.999982f, 0.999983f, 0.999984f, 0.999986f, 0.999987f, 0.999988f, 0.999989f, 0.999990f, 0.999990f,
+    0.999991f, 0.999992f, 0.999992f, 0.999993f, 0.999994f, 0.999994f, 0.999994f, 0.999995f, 0.999995f, 0.999996f, 0.999996f,
+    0.999996f, 0.999997f, 0.999997f, 0.999997f, 0.999997f, 0.999997f, 0.999998f, 0.999998f, 0.999998f, 0.999998f, 0.999998f,
+    0.999998f, 0.999999f, 0.999999f, 0.999999f, 0.999999f, 0.999999f, 0.999999f, 0.999999f, 0.999999f, 0.999999f, 0.999999f,
+    0.999999f, 0.999999f, 0.999999f, 1.000000f, 1.000000f, 1.000000f, 1.000000f, 1.000000f, 1.000000f, 1.000000f, 1.000000f,
+    1.000000f, 1.000000f, 1.000000f,
+};
+const int kEband5ms[NB_BANDS] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 34, 40, 48, 60, 78, 100};
+
+void build_tables(DeviceTables* t) {
+    std::memset(t, 0, sizeof(*t));
+    const double pi = 3.14159265358979323846264338327950288;
+    for (int i = 0; i < FRAME_SIZE; i++) {
+        double s = std::sin(0.5 * pi * ((double)i + 0.5) / (double)FRAME_SIZE);
+        float w = (float)std::sin(0.5 * pi * s * s);
+        t->window[i] = w;
+        t->window[WINDOW_SIZE - i - 1] = w;
+    }
+    volatile float acc = 0.0f;  // f32 sequential sum (src/lib.rs:116)
+    for (int i = 0; i < WINDOW_SIZE; i++) acc = acc + t->window[i] * t->window[i];
+    t->wnorm = 1.0f / acc;
+    for (int i = 0; i < NB_BANDS; i++)
+        for (int j = 0; j < NB_BANDS; j++) {
+            float v = (float)std::cos(((double)i + 0.5) * (double)j * pi / (double)NB_BANDS);
+            if (j == 0) v *= std::sqrt(0.5f);
+            t->dct[i * NB_BANDS + j] = v;
+        }
+    for (int i = 0; i < 201; i++) t->tansig[i] = kTansig[i];
+    for (int k = 0; k < 480; k++)
+        t->tw480[k] = make_float2((float)std::cos(-2.0 * pi * (double)k / 480.0), (float)std::sin(-2.0 * pi * (double)k / 480.0));
+    for (int k = 0; k <= 480; k++)
+        t->tw960[k] = make_float2((float)std::cos(-2.0 * pi * (double)k / 960.0), (float)std::sin(-2.0 * pi * (double)k / 960.0));
+    for (int i = 0; i < NB_BANDS; i++) t->band_start[i] = kEband5ms[i] << 2;
+    for (int i = 0; i < NB_BANDS - 1; i++) {
+        int band_size = (kEband5ms[i + 1] - kEband5ms[i]) << 2;
+        for (int j = 0; j < band_size; j++) {
+            int idx = (kEband5ms[i] << 2) + j;
+            t->band_frac[idx] = (float)j / (float)band_size;
+            t->band_of[idx] = i;
+        }
+    }
+}
+
+// ---- model upload: int8 -> f32, GRU matrices regrouped per phase (see common.cuh DeviceLayer) ----------
+struct UploadedModel {
+    DeviceModel dm{};
+    float* d_blob = nullptr;
+};
+
+size_t dense_floats(const HostDense& l) { return (size_t)l.ni * l.nn + l.nn; }
+size_t gru_floats(const HostGru& l) { return (size_t)(l.ni + l.nn) * 3 * l.nn + 3 * l.nn; }
+
+void fill_dense(const HostModel& m, const HostDense& l, std::vector<float>& blob, size_t* off, DeviceLayer* out, float* dbase) {
+    const int8_t* w = m.bytes.data() + l.w_off;
+    const int8_t* b = m.bytes.data() + l.b_off;
+    out->ni = l.ni;
+    out->nn = l.nn;
+    out->act = l.act;
+    out->w = dbase + *off;
+    for (size_t i = 0; i < (size_t)l.ni * l.nn; i++) blob[(*off)++] = (float)w[i];
+    out->wh = nullptr;
+    out->bias = dbase + *off;
+    for (int i = 0; i < l.nn; i++) blob[(*off)++] = (float)b[i];
+}
+
+void fill_gru(const HostModel& m, const HostGru& l, std::vector<float>& blob, size_t* off, DeviceLayer* out, float* dbase) {
+    const int8_t* w = m.bytes.data() + l.w_off;
+    const int8_t* r = m.bytes.data() + l.r_off;
+    const int8_t* b = m.bytes.data() + l.b_off;
+    const int ni = l.ni, nn = l.nn, st = 3 * nn;
+    out->ni = ni;
+    out->nn = nn;
+    out->act = l.act;
+    out->w = dbase + *off;  // wzr [(ni+nn)][2nn]
+    for (int j = 0; j < ni; j++)
+        for (int o = 0; o < 2 * nn; o++) blob[(*off)++] = (float)w[(size_t)j * st + o];
+    for (int j = 0; j < nn; j++)
+        for (int o = 0; o < 2 * nn; o++) blob[(*off)++] = (float)r[(size_t)j * st + o];
+    out->wh = dbase + *off;  // wh [(ni+nn)][nn]
+    for (int j = 0; j < ni; j++)
+        for (int o = 0; o < nn; o++) blob[(*off)++] = (float)w[(size_t)j * st + 2 * nn + o];
+    for (int j = 0; j < nn; j++)
+        for (int o = 0; o < nn; o++) blob[(*off)++] = (float)r[(size_t)j * st + 2 * nn + o];
+    out->bias = dbase + *off;
+    for (int i = 0; i < st; i++) blob[(*off)++] = (float)b[i];
+}
+
+int upload_model(const HostModel& m, UploadedModel* um, cudaStream_t st) {
+    size_t total = dense_floats(m.input_dense) + gru_floats(m.vad_gru) + gru_floats(m.noise_gru) + gru_floats(m.denoise_gru) +
+                   dense_floats(m.denoise_output) + dense_floats(m.vad_output);
+    std::vector<float> blob(total);
+    CK(cudaMalloc(&um->d_blob, total * sizeof(float)));
+    size_t off = 0;
+    fill_dense(m, m.input_dense, blob, &off, &um->dm.input_dense, um->d_blob);
+    fill_gru(m, m.vad_gru, blob, &off, &um->dm.vad_gru, um->d_blob);
+    fill_gru(m, m.noise_gru, blob, &off, &um->dm.noise_gru, um->d_blob);
+    fill_gru(m, m.denoise_gru, blob, &off, &um->dm.denoise_gru, um->d_blob);
+    fill_dense(m, m.denoise_output, blob, &off, &um->dm.denoise_output, um->d_blob);
+    fill_dense(m, m.vad_output, blob, &off, &um->dm.vad_output, um->d_blob);
+    um->dm.state_size = m.vad_gru.nn + m.noise_gru.nn + m.denoise_gru.nn;
+    CK(cudaMemcpyAsync(um->d_blob, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- pcm16 front-end kernels (src/nnnoiseless.rs:147-177, test_data/rnnoise_demo.c:51-55) ---------------
+__global__ void pcm16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+__global__ void f32_to_pcm16_kernel(const float* __restrict__ in, short* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float v = fminf(fmaxf(in[i], -32768.0f), 32767.0f);  // clamp, then round half away from zero
+        out[i] = (short)roundf(v);
+    }
+}
+
+}  // namespace
+
+// ---- the batch handle -----------------------------------------------------------------------------------
+struct RNNoiseBatch {
+    int device = 0;
+    int n_streams = 0;
+    cudaStream_t stream = nullptr;
+    BatchBuffers buf{};
+    std::vector<void*> allocs;
+    DeviceTables* d_tab = nullptr;
+    UploadedModel um;
+    unsigned long long frame = 0;  // frames processed so far (ring slot = frame % HIST_SLOTS)
+    // host-call staging
+    float* stage_in = nullptr;
+    float* stage_out = nullptr;
+    float* stage_vad = nullptr;
+    short* stage_pcm = nullptr;
+    int stage_frames = 0;
+    bool stage_has_pcm = false;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(RNNoiseBatch* b, T** p, size_t count) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, count * sizeof(T)));
+    b->allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+
+int zero_state(RNNoiseBatch* b) {
+    const size_t B = (size_t)b->n_streams;
+    BatchBuffers& u = b->buf;
+    const int SS = b->um.dm.state_size;
+    CK(cudaMemsetAsync(u.hist, 0, B * HIST_CAP * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.hp_mem, 0, B * 2 * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.synth_mem, 0, B * FRAME_SIZE * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.ceps_mem, 0, B * CEPS_MEM * NB_BANDS * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.ceps_id, 0, B * sizeof(int32_t), b->stream));
+    CK(cudaMemsetAsync(u.last_period, 0, B * sizeof(int32_t), b->stream));
+    CK(cudaMemsetAsync(u.last_gain, 0, B * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.gru_state, 0, B * SS * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.lastg, 0, B * NB_BANDS * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.gains, 0, B * NB_BANDS * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.vad, 0, B * sizeof(float), b->stream));
+    CK(cudaMemsetAsync(u.silence, 0, B * sizeof(int32_t), b->stream));
+    CK(cudaMemsetAsync(u.pitch, 0, B * sizeof(int32_t), b->stream));
+    CK(cudaMemsetAsync(u.features, 0, B * NB_FEATURES * sizeof(float), b->stream));
+    b->frame = 0;
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail("no CUDA device available (this library has no CPU fallback)", e);
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= ndev) return fail("device index out of range");
+    if (n_streams <= 0) return fail("n_streams must be positive");
+    CK(cudaSetDevice(device));
+    b->device = device;
+    b->n_streams = n_streams;
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    const size_t B = (size_t)n_streams;
+    BatchBuffers& u = b->buf;
+    u.n_streams = n_streams;
+    if (upload_model(hm, &b->um, b->stream)) return -1;
+    b->allocs.push_back(b->um.d_blob);
+    const int SS = b->um.dm.state_size;
+    if (dalloc(b, &u.hist, B * HIST_CAP) || dalloc(b, &u.hp_mem, B * 2) || dalloc(b, &u.synth_mem, B * FRAME_SIZE) ||
+        dalloc(b, &u.ceps_mem, B * CEPS_MEM * NB_BANDS) || dalloc(b, &u.ceps_id, B) || dalloc(b, &u.last_period, B) ||
+        dalloc(b, &u.last_gain, B) || dalloc(b, &u.gru_state, B * SS) || dalloc(b, &u.lastg, B * NB_BANDS) ||
+        dalloc(b, &u.X, B * FREQ_SIZE) || dalloc(b, &u.P, B * NB_BINS_BANDED) || dalloc(b, &u.ex, B * NB_BANDS) ||
+        dalloc(b, &u.ep, B * NB_BANDS) || dalloc(b, &u.exp, B * NB_BANDS) || dalloc(b, &u.features, B * NB_FEATURES) ||
+        dalloc(b, &u.silence, B) || dalloc(b, &u.pitch, B) || dalloc(b, &u.gains, B * NB_BANDS) || dalloc(b, &u.vad, B) ||
+        dalloc(b, &b->d_tab, 1))
+        return -1;
+    DeviceTables* ht = new DeviceTables();
+    build_tables(ht);
+    cudaError_t ce = cudaMemcpyAsync(b->d_tab, ht, sizeof(DeviceTables), cudaMemcpyHostToDevice, b->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
+    delete ht;
+    if (ce != cudaSuccess) return fail("table upload", ce);
+    return zero_state(b);
+}
+
+void batch_release(RNNoiseBatch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void* p : b->allocs) cudaFree(p);
+    b->allocs.clear();
+    if (b->stage_in) cudaFree(b->stage_in);
+    if (b->stage_out) cudaFree(b->stage_out);
+    if (b->stage_vad) cudaFree(b->stage_vad);
+    if (b->stage_pcm) cudaFree(b->stage_pcm);
+    b->stage_in = b->stage_out = b->stage_vad = nullptr;
+    b->stage_pcm = nullptr;
+    if (b->stream) cudaStreamDestroy(b->stream);
+    b->stream = nullptr;
+}
+
+int ensure_stage(RNNoiseBatch* b, int n_frames, bool pcm) {
+    if (n_frames > b->stage_frames || (pcm && !b->stage_has_pcm)) {
+        CK(cudaStreamSynchronize(b->stream));
+        const int nf = n_frames > b->stage_frames ? n_frames : b->stage_frames;
+        if (b->stage_in) cudaFree(b->stage_in);
+        if (b->stage_out) cudaFree(b->stage_out);
+        if (b->stage_vad) cudaFree(b->stage_vad);
+        if (b->stage_pcm) cudaFree(b->stage_pcm);
+        b->stage_in = b->stage_out = b->stage_vad = nullptr;
+        b->stage_pcm = nullptr;
+        b->stage_frames = 0;
+        size_t n = (size_t)nf * b->n_streams;
+        CK(cudaMalloc(&b->stage_in, n * FRAME_SIZE * sizeof(float)));
+        CK(cudaMalloc(&b->stage_out, n * FRAME_SIZE * sizeof(float)));
+        CK(cudaMalloc(&b->stage_vad, n * sizeof(float)));
+        if (pcm || b->stage_has_pcm) {
+            CK(cudaMalloc(&b->stage_pcm, n * FRAME_SIZE * sizeof(short)));
+            b->stage_has_pcm = true;
+        }
+        b->stage_frames = nf;
+    }
+    return 0;
+}
+
+// One frame for all streams: the five kernels of the path.
+int step(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, cudaStream_t st) {
+    const int slot = (int)(b->frame % HIST_SLOTS);
+    CK(launch_hp_filter(b->buf, in, stream_stride, slot, st));
+    CK(launch_pitch(b->buf, slot, st));
+    CK(launch_analysis(b->buf, b->d_tab, slot, st));
+    CK(launch_rnn(b->buf, b->um.dm, b->d_tab, st));
+    CK(launch_synthesis(b->buf, b->d_tab, out, stream_stride, vad, st));
+    g_launches.fetch_add(5, std::memory_order_relaxed);
+    b->frame++;
+    return 0;
+}
+
+}  // namespace
+
+// ============================================================================================== C ABI
+extern "C" {
+
+const char* rnnoise_last_error(void) { return g_err.c_str(); }
+unsigned long long rnnoise_kernel_launches(void) { return g_launches.load(); }
+
+RNNModel* rnnoise_model_from_bytes(const unsigned char* bytes, size_t len) {
+    RNNModel* m = new (std::nothrow) RNNModel();
+    if (!m) return nullptr;
+    if (!bytes || !HostModel::parse(bytes, len, &m->m)) {
+        delete m;
+        fail("model bytes rejected (src/rnn.rs:116-232 validation)");
+        return nullptr;
+    }
+    return m;
+}
+
+RNNModel* rnnoise_model_from_text(const char* text, size_t len) {
+    RNNModel* m = new (std::nothrow) RNNModel();
+    if (!m) return nullptr;
+    if (!text || !HostModel::parse_text(text, len, &m->m)) {
+        delete m;
+        fail("text model rejected");
+        return nullptr;
+    }
+    return m;
+}
+
+RNNModel* rnnoise_model_from_file(FILE* file) {
+    if (!file) return nullptr;
+    std::vector<unsigned char> data;
+    unsigned char chunk[65536];
+    size_t n;
+    bool err = false;
+    while ((n = fread(chunk, 1, sizeof chunk, file)) > 0) data.insert(data.end(), chunk, chunk + n);
+    if (ferror(file)) err = true;
+    fclose(file);  // the reference takes the FILE over and closes it (src/capi.rs:93-94)
+    if (err) return nullptr;
+    return rnnoise_model_from_bytes(data.data(), data.size());
+}
+
+void rnnoise_model_free(RNNModel* model) { delete model; }
+
+size_t rnnoise_model_bytes(const RNNModel* model, unsigned char* buf, size_t cap) {
+    const HostModel& m = model ? model->m : HostModel::builtin();
+    if (buf && cap >= m.bytes.size()) std::memcpy(buf, m.bytes.data(), m.bytes.size());
+    return m.bytes.size();
+}
+
+RNNoiseBatch* rnnoise_batch_create(const RNNModel* model, int n_streams, int device) {
+    RNNoiseBatch* b = new (std::nothrow) RNNoiseBatch();
+    if (!b) return nullptr;
+    const HostModel& hm = model ? model->m : HostModel::builtin();
+    if (batch_init(b, hm, n_streams, device) != 0) {
+        std::string keep = g_err;
+        batch_release(b);
+        delete b;
+        g_err = keep;
+        return nullptr;
+    }
+    return b;
+}
+
+void rnnoise_batch_destroy(RNNoiseBatch* b) {
+    if (!b) return;
+    batch_release(b);
+    delete b;
+}
+
+int rnnoise_batch_streams(const RNNoiseBatch* b) { return b ? b->n_streams : 0; }
+
+int rnnoise_batch_reset(RNNoiseBatch* b) {
+    if (!b) return fail("null batch");
+    CK(cudaSetDevice(b->device));
+    return zero_state(b);
+}
+
+int rnnoise_batch_process_device(RNNoiseBatch* b, float* out, const float* in, float* vad, int n_frames, long stream_stride,
+                                 long frame_stride, void* cuda_stream) {
+    if (!b || !out || !in) return fail("null argument");
+    if (n_frames < 0) return fail("negative n_frames");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+    for (int t = 0; t < n_frames; t++) {
+        if (step(b, out + (long)t * frame_stride, in + (long)t * frame_stride, vad ? vad + (size_t)t * b->n_streams : nullptr,
+                 stream_stride, st))
+            return -1;
+    }
+    if (!cuda_stream) CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int rnnoise_batch_process_host(RNNoiseBatch* b, float* out, const float* in, float* vad, int n_frames) {
+    if (!b || !out || !in) return fail("null argument");
+    if (n_frames <= 0) return n_frames == 0 ? 0 : fail("negative n_frames");
+    CK(cudaSetDevice(b->device));
+    if (ensure_stage(b, n_frames, false)) return -1;
+    const size_t n = (size_t)n_frames * b->n_streams;
+    const long fs = (long)b->n_streams * FRAME_SIZE;
+    CK(cudaMemcpyAsync(b->stage_in, in, n * FRAME_SIZE * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    for (int t = 0; t < n_frames; t++)
+        if (step(b, b->stage_out + t * fs, b->stage_in + t * fs, b->stage_vad + (size_t)t * b->n_streams, FRAME_SIZE, b->stream))
+            return -1;
+    CK(cudaMemcpyAsync(out, b->stage_out, n * FRAME_SIZE * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    if (vad) CK(cudaMemcpyAsync(vad, b->stage_vad, n * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int rnnoise_batch_process_pcm16_host(RNNoiseBatch* b, short* out, const short* in, float* vad, int n_frames) {
+    if (!b || !out || !in) return fail("null argument");
+    if (n_frames <= 0) return n_frames == 0 ? 0 : fail("negative n_frames");
+    CK(cudaSetDevice(b->device));
+    if (ensure_stage(b, n_frames, true)) return -1;
+    const size_t n = (size_t)n_frames * b->n_streams;
+    const size_t ns = n * FRAME_SIZE;
+    const long fs = (long)b->n_streams * FRAME_SIZE;
+    const int th = 256;
+    const unsigned grid = (unsigned)((ns + th - 1) / th);
+    CK(cudaMemcpyAsync(b->stage_pcm, in, ns * sizeof(short), cudaMemcpyHostToDevice, b->stream));
+    pcm16_to_f32_kernel<<<grid, th, 0, b->stream>>>(b->stage_pcm, b->stage_in, ns);
+    CK(cudaGetLastError());
+    for (int t = 0; t < n_frames; t++)
+        if (step(b, b->stage_out + t * fs, b->stage_in + t * fs, b->stage_vad + (size_t)t * b->n_streams, FRAME_SIZE, b->stream))
+            return -1;
+    f32_to_pcm16_kernel<<<grid, th, 0, b->stream>>>(b->stage_out, b->stage_pcm, ns);
+    CK(cudaGetLastError());
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    CK(cudaMemcpyAsync(out, b->stage_pcm, ns * sizeof(short), cudaMemcpyDeviceToHost, b->stream));
+    if (vad) CK(cudaMemcpyAsync(vad, b->stage_vad, n * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int rnnoise_batch_get_taps(RNNoiseBatch* b, int* pitch, int* silence, float* features, float* gains) {
+    if (!b) return fail("null batch");
+    CK(cudaSetDevice(b->device));
+    const size_t B = (size_t)b->n_streams;
+    CK(cudaStreamSynchronize(b->stream));
+    if (pitch) CK(cudaMemcpy(pitch, b->buf.pitch, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (silence) CK(cudaMemcpy(silence, b->buf.silence, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (features) CK(cudaMemcpy(features, b->buf.features, B * NB_FEATURES * sizeof(float), cudaMemcpyDeviceToHost));
+    if (gains) CK(cudaMemcpy(gains, b->buf.lastg, B * NB_BANDS * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- legacy single-stream API (src/capi.rs) = a batch of one ------------------------------------------
+struct DenoiseState {
+    RNNoiseBatch* batch;
+};
+
+int rnnoise_get_frame_size(void) { return FRAME_SIZE; }
+int rnnoise_get_size(void) { return (int)sizeof(DenoiseState); }
+
+int rnnoise_init(DenoiseState* st, RNNModel* model) {
+    if (!st) return fail("null state");
+    st->batch = rnnoise_batch_create(model, 1, -1);
+    return st->batch ? 0 : -1;
+}
+
+DenoiseState* rnnoise_create(RNNModel* model) {
+    DenoiseState* st = new (std::nothrow) DenoiseState();
+    if (!st) return nullptr;
+    if (rnnoise_init(st, model) != 0) {
+        delete st;
+        return nullptr;
+    }
+    return st;
+}
+
+void rnnoise_destroy(DenoiseState* st) {
+    if (!st) return;
+    rnnoise_batch_destroy(st->batch);
+    delete st;
+}
+
+float rnnoise_process_frame(DenoiseState* st, float* out, float* in) {
+    if (!st || !st->batch) {
+        fprintf(stderr, "rnnoise_process_frame: Invalid pointer\n");  // the reference panics (src/capi.rs:80)
+        abort();
+    }
+    float vad = 0.0f;
+    if (rnnoise_batch_process_host(st->batch, out, in, &vad, 1) != 0) {
+        fprintf(stderr, "rnnoise_process_frame: %s\n", g_err.c_str());
+        abort();  // no CPU fallback: a CUDA failure is fatal, like a panic across the FFI
+    }
+    return vad;
+}
+
+}  // extern "C"

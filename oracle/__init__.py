@@ -16,13 +16,34 @@ NB_BANDS = 22
 NB_FEATURES = 42
 
 
+def _cpu_stamp():
+    """The Makefile uses -march=native: rebuild when the host CPU differs from the one that built the .so."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        model = [l for l in txt.splitlines() if l.startswith("model name")][:1]
+        flags = [l for l in txt.splitlines() if l.startswith("flags")][:1]
+        return "|".join(model + flags)
+    except OSError:
+        return "unknown"
+
+
 def build(force=False):
     """Compile oracle/nno_oracle.c with gcc (see oracle/Makefile)."""
     src = [os.path.join(_HERE, f) for f in ("nno_oracle.c", "nno_oracle.h", "Makefile")]
-    if (not force and os.path.exists(_LIB_PATH)
+    stamp_path = os.path.join(_HERE, "_build", "cpu.stamp")
+    stamp = _cpu_stamp()
+    try:
+        with open(stamp_path) as f:
+            same_cpu = f.read() == stamp
+    except OSError:
+        same_cpu = False
+    if (not force and same_cpu and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
     subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    with open(stamp_path, "w") as f:
+        f.write(stamp)
     return _LIB_PATH
 
 
@@ -46,8 +67,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()
         L = C.CDLL(_LIB_PATH)
         L.nno_model_from_bytes.restype = C.c_void_p
         L.nno_model_from_bytes.argtypes = [C.c_char_p, C.c_size_t]

@@ -108,6 +108,14 @@ int rnnoise_batch_process_pcm16_host(RNNoiseBatch *b, short *out, const short *i
  *   (gains after the 0.6*lastg floor). */
 int rnnoise_batch_get_taps(RNNoiseBatch *b, int *pitch, int *silence, float *features, float *gains);
 
+/* Profiling aid: advance every stream by ONE frame like rnnoise_batch_process_device, with CUDA events
+ * recorded between the kernels of the path on the launching stream; synchronises and writes each
+ * kernel's duration in milliseconds to ms[0..n) (n = return value <= cap; negative on error).
+ * rnnoise_kernel_name(i) names kernel i of the path (NULL past the end). */
+int rnnoise_batch_profile_step(RNNoiseBatch *b, float *out, const float *in, float *vad, long stream_stride,
+                               void *cuda_stream, float *ms, int cap);
+const char *rnnoise_kernel_name(int i);
+
 /* Number of kernel launches issued by this library since load (bench evidence). */
 unsigned long long rnnoise_kernel_launches(void);
 

@@ -30,7 +30,8 @@ C_ABI_SYMBOLS = [
     "rnnoise_model_from_bytes", "rnnoise_model_from_text", "rnnoise_model_bytes",
     "rnnoise_batch_create", "rnnoise_batch_destroy", "rnnoise_batch_streams", "rnnoise_batch_reset",
     "rnnoise_batch_process_device", "rnnoise_batch_process_host", "rnnoise_batch_process_pcm16_host",
-    "rnnoise_batch_get_taps", "rnnoise_kernel_launches", "rnnoise_last_error",
+    "rnnoise_batch_get_taps", "rnnoise_batch_profile_step", "rnnoise_kernel_name",
+    "rnnoise_kernel_launches", "rnnoise_last_error",
 ]
 
 _lib = None
@@ -83,6 +84,10 @@ def lib():
     L.rnnoise_batch_process_pcm16_host.argtypes = [vp, vp, vp, vp, ci]
     L.rnnoise_batch_get_taps.restype = ci
     L.rnnoise_batch_get_taps.argtypes = [vp, vp, vp, vp, vp]
+    L.rnnoise_batch_profile_step.restype = ci
+    L.rnnoise_batch_profile_step.argtypes = [vp, vp, vp, vp, C.c_long, vp, vp, ci]
+    L.rnnoise_kernel_name.restype = C.c_char_p
+    L.rnnoise_kernel_name.argtypes = [ci]
     L.rnnoise_kernel_launches.restype = C.c_ulonglong
     L.rnnoise_last_error.restype = C.c_char_p
     _lib = L
@@ -220,6 +225,16 @@ class DenoiseBatch:
                                                 C.c_void_p(cuda_stream) if cuda_stream else None)
         if rc != 0:
             raise NnnoiselessError(last_error())
+
+    def profile_step(self, out_ptr: int, in_ptr: int, vad_ptr: int, stream_stride: int, cuda_stream: int = 0):
+        """One frame with CUDA events between the kernels: returns {kernel name: milliseconds}."""
+        ms = (C.c_float * 16)()
+        n = lib().rnnoise_batch_profile_step(self._h, C.c_void_p(out_ptr), C.c_void_p(in_ptr),
+                                             C.c_void_p(vad_ptr) if vad_ptr else None, int(stream_stride),
+                                             C.c_void_p(cuda_stream) if cuda_stream else None, ms, 16)
+        if n < 0:
+            raise NnnoiselessError(last_error())
+        return {lib().rnnoise_kernel_name(i).decode(): float(ms[i]) for i in range(n)}
 
     def taps(self):
         """Intermediates of the most recent frame: dict(pitch, silence, features, gains)."""

@@ -304,15 +304,26 @@ int ensure_stage(RNNoiseBatch* b, int n_frames, bool pcm) {
     return 0;
 }
 
-// One frame for all streams: the five kernels of the path.
-int step(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, cudaStream_t st) {
+constexpr int kNumKernels = 5;
+const char* const kKernelNames[kNumKernels] = {"hp_filter", "pitch", "analysis", "rnn", "synthesis"};
+
+// One frame for all streams: the five kernels of the path.  ev (optional): kNumKernels + 1 events
+// recorded around the kernels.
+int step(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, cudaStream_t st,
+         cudaEvent_t* ev = nullptr) {
     const int slot = (int)(b->frame % HIST_SLOTS);
+    if (ev) CK(cudaEventRecord(ev[0], st));
     CK(launch_hp_filter(b->buf, in, stream_stride, slot, st));
+    if (ev) CK(cudaEventRecord(ev[1], st));
     CK(launch_pitch(b->buf, slot, st));
+    if (ev) CK(cudaEventRecord(ev[2], st));
     CK(launch_analysis(b->buf, b->d_tab, slot, st));
+    if (ev) CK(cudaEventRecord(ev[3], st));
     CK(launch_rnn(b->buf, b->um.dm, b->d_tab, st));
+    if (ev) CK(cudaEventRecord(ev[4], st));
     CK(launch_synthesis(b->buf, b->d_tab, out, stream_stride, vad, st));
-    g_launches.fetch_add(5, std::memory_order_relaxed);
+    if (ev) CK(cudaEventRecord(ev[5], st));
+    g_launches.fetch_add(kNumKernels, std::memory_order_relaxed);
     b->frame++;
     return 0;
 }
@@ -409,6 +420,27 @@ int rnnoise_batch_process_device(RNNoiseBatch* b, float* out, const float* in, f
     }
     if (!cuda_stream) CK(cudaStreamSynchronize(st));
     return 0;
+}
+
+const char* rnnoise_kernel_name(int i) { return (i >= 0 && i < kNumKernels) ? kKernelNames[i] : nullptr; }
+
+int rnnoise_batch_profile_step(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, void* cuda_stream,
+                               float* ms, int cap) {
+    if (!b || !out || !in || !ms) return fail("null argument");
+    if (cap < kNumKernels) return fail("ms[] too small");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+    cudaEvent_t ev[kNumKernels + 1];
+    for (int i = 0; i <= kNumKernels; i++) CK(cudaEventCreate(&ev[i]));
+    int rc = step(b, out, in, vad, stream_stride, st, ev);
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail("profile_step sync", e);
+    }
+    if (rc == 0)
+        for (int i = 0; i < kNumKernels; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (int i = 0; i <= kNumKernels; i++) cudaEventDestroy(ev[i]);
+    return rc == 0 ? kNumKernels : rc;
 }
 
 int rnnoise_batch_process_host(RNNoiseBatch* b, float* out, const float* in, float* vad, int n_frames) {

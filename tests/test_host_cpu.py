@@ -1,0 +1,104 @@
+"""CPU tests of the product's host side: the C-ABI library loads without a GPU, exports every symbol
+include/rnnoise.h declares, parses models exactly like the reference, and refuses to run without CUDA."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nnnoiseless_b200 as nb
+import oracle
+from conftest import ROOT
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "rnnoise.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(rnnoise_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(nb.C_ABI_SYMBOLS)
+    L = nb.lib()
+    for sym in declared:
+        assert getattr(L, sym) is not None
+
+
+def test_reference_abi_basics():
+    L = nb.lib()
+    assert L.rnnoise_get_frame_size() == 480  # src/capi.rs:17-19
+    assert L.rnnoise_get_size() > 0
+
+
+def _mutations(good: bytes):
+    yield good[:-1]                      # truncated
+    yield good + b"\x00"                 # trailing byte (src/rnn.rs:196-198)
+    yield b""                            # empty
+    yield b"\x2a\x18"                    # short header
+    bad = bytearray(good); bad[0] = 41; yield bytes(bad)          # input_dense.ni != 42
+    bad = bytearray(good); bad[2] = 3; yield bytes(bad)           # unknown activation
+    bad = bytearray(good); bad[1] = 0x80; yield bytes(bad)        # negative neuron count
+    bad = bytearray(good); bad[1035 + 1] = 25; yield bytes(bad)   # vad_gru.nn changes -> sizes no longer chain
+
+
+def test_model_parser_matches_oracle(builtin_bytes, sh_bytes):
+    for good in (builtin_bytes, sh_bytes):
+        m = nb.RnnModel.from_bytes(good)
+        assert m is not None and m.to_bytes() == good and oracle.model_accepts(good)
+        for bad in _mutations(good):
+            assert nb.RnnModel.from_bytes(bad) is None
+            assert not oracle.model_accepts(bad)
+
+
+def test_builtin_model_is_weights_rnn(builtin_bytes):
+    assert nb.RnnModel().to_bytes() == builtin_bytes and len(builtin_bytes) == 87521
+
+
+def test_text_model_conversion(sh_bytes):
+    """train/convert_rnnoise.py:18-29 semantics on a synthetic text file built from the fixture."""
+    ints = np.frombuffer(sh_bytes, dtype=np.int8)
+    text = "rnnoise-nu model file version 1\n" + " ".join(str(int(v)) for v in ints) + "\n"
+    m = nb.RnnModel.from_text(text)
+    assert m is not None and m.to_bytes() == sh_bytes
+    assert nb.RnnModel.from_text("wrong header\n1 2 3") is None
+    assert nb.RnnModel.from_text("rnnoise-nu model file version 1\n1 2 x") is None
+
+
+def test_model_from_file_takes_over_file(tmp_path, builtin_bytes):
+    p = tmp_path / "m.rnn"
+    p.write_bytes(builtin_bytes)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    f = libc.fopen(str(p).encode(), b"rb")
+    h = nb.lib().rnnoise_model_from_file(f)  # closes f (src/capi.rs:93-94)
+    assert h
+    nb.lib().rnnoise_model_free(h)
+    p.write_bytes(builtin_bytes[:100])
+    f = libc.fopen(str(p).encode(), b"rb")
+    assert not nb.lib().rnnoise_model_from_file(f)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(nb.NnnoiselessError, match="no CUDA device"):
+        nb.DenoiseBatch(4)
+    with pytest.raises(nb.NnnoiselessError):
+        nb.DenoiseState()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "nnnoiseless_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "import oracle" not in txt and "nno_oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_shard_streams_partition():
+    for n, w in [(262144, 8), (65536, 3), (5, 8), (37, 4)]:
+        spans = [nb.shard_streams(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+        for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+            assert s0 + c0 == s1

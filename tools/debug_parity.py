@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle
 import nnnoiseless_b200 as nb
-from conftest import synth_streams, golden_metric
+from conftest import golden_metric
 
 mb = open(nb.BUILTIN_WEIGHTS_PATH, "rb").read()
 om = oracle.Model(mb)

@@ -52,22 +52,22 @@ __device__ __forceinline__ void butterfly(float2* a) {
     }
 }
 
-// One Stockham DIF pass: n = current sub-length, s = product of the previous radices.
-template <int R>
-__device__ __forceinline__ void stockham_pass(int n, int s, const float2* __restrict__ x, float2* __restrict__ y,
+// One Stockham DIF pass of radix R on sub-length N with stride S = 480 / N (product of previous radices).
+template <int R, int N, int S>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ x, float2* __restrict__ y,
                                               const float2* __restrict__ tw) {
-    const int m = n / R;
+    constexpr int M = N / R;
     for (int b = threadIdx.x; b < 480 / R; b += ST) {
-        int p = b / s, q = b - p * s;
+        const int p = b / S, q = b - p * S;
         float2 a[R];
 #pragma unroll
-        for (int k = 0; k < R; k++) a[k] = x[q + s * (p + k * m)];
+        for (int k = 0; k < R; k++) a[k] = x[q + S * (p + k * M)];
         butterfly<R>(a);
-        y[q + s * (R * p)] = a[0];
+        y[q + S * (R * p)] = a[0];
 #pragma unroll
         for (int j = 1; j < R; j++) {
-            int idx = (j * p * s) % 480;
-            y[q + s * (R * p + j)] = cmul(a[j], tw[idx]);
+            // twiddle exp(-2 pi i j p / N) = tw480[j p S];  j p S < 480 because p < N / R
+            y[q + S * (R * p + j)] = (N == R) ? a[j] : cmul(a[j], __ldg(&tw[j * p * S]));
         }
     }
     __syncthreads();
@@ -75,30 +75,34 @@ __device__ __forceinline__ void stockham_pass(int n, int s, const float2* __rest
 
 // forward FFT of a[480]; result lands in b.  Both buffers in shared memory; tw = tw480 table.
 __device__ void fft480(float2* a, float2* b, const float2* tw) {
-    stockham_pass<4>(480, 1, a, b, tw);
-    stockham_pass<4>(120, 4, b, a, tw);
-    stockham_pass<5>(30, 16, a, b, tw);
-    stockham_pass<3>(6, 80, b, a, tw);
-    stockham_pass<2>(2, 240, a, b, tw);
+    stockham_pass<4, 480, 1>(a, b, tw);
+    stockham_pass<4, 120, 4>(b, a, tw);
+    stockham_pass<5, 30, 16>(a, b, tw);
+    stockham_pass<3, 6, 80>(b, a, tw);
+    stockham_pass<2, 2, 240>(a, b, tw);
 }
 
 // Band-weighted correlation (src/lib.rs:65-82).  cb[0..400) holds Re(x conj p) per bin.
-// Thread t < 22 produces band t summing, in the reference's order, first the `frac` part of
-// segment t-1 and then the `1-frac` part of segment t.
+// Band t = frac-weighted part of segment t-1 plus (1-frac)-weighted part of segment t.  Four lanes per
+// band (threads 0..87), partial sums combined with shuffles; call with all threads of warps 0-2.
 __device__ void band_sums(const float* cb, const DeviceTables* __restrict__ tab, float* out) {
-    const int t = threadIdx.x;
-    if (t < NB_BANDS) {
+    const int tid = threadIdx.x;
+    if (tid < 96) {
+        const int t = tid >> 2, part = tid & 3;
         float acc = 0.0f;
-        if (t > 0) {
-            int lo = tab->band_start[t - 1], hi = tab->band_start[t];
-            for (int i = lo; i < hi; i++) acc += tab->band_frac[i] * cb[i];
+        if (t < NB_BANDS) {
+            if (t > 0) {
+                const int lo = tab->band_start[t - 1], hi = tab->band_start[t];
+                for (int i = lo + part; i < hi; i += 4) acc += __ldg(&tab->band_frac[i]) * cb[i];
+            }
+            if (t < NB_BANDS - 1) {
+                const int lo = tab->band_start[t], hi = tab->band_start[t + 1];
+                for (int i = lo + part; i < hi; i += 4) acc += (1.0f - __ldg(&tab->band_frac[i])) * cb[i];
+            }
         }
-        if (t < NB_BANDS - 1) {
-            int lo = tab->band_start[t], hi = tab->band_start[t + 1];
-            for (int i = lo; i < hi; i++) acc += (1.0f - tab->band_frac[i]) * cb[i];
-        }
-        if (t == 0 || t == NB_BANDS - 1) acc *= 2.0f;
-        out[t] = acc;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (t < NB_BANDS && part == 0) out[t] = (t == 0 || t == NB_BANDS - 1) ? 2.0f * acc : acc;
     }
 }
 
@@ -198,16 +202,20 @@ __global__ void __launch_bounds__(ST) analysis_kernel(BatchBuffers bb, const Dev
         for (int j = 0; j < NB_BANDS; j++) sum += s_exp[j] * tab->dct[j * NB_BANDS + tid];
         s_tmp[tid] = (float)((double)sum * dct_scale);
     }
-    if (tid == 32) {  // another warp: log band energies, sequential follower (src/features.rs:147-158)
+    if (tid >= 32 && tid < 64) {  // another warp: log band energies, sequential follower (src/features.rs:147-158)
+        const int i = tid - 32;
+        float lg = (i < NB_BANDS) ? log10f(1e-2f + s_ex[i]) : 0.0f;
+        float exi = (i < NB_BANDS) ? s_ex[i] : 0.0f;
         float log_max = -2.0f, follow = -2.0f, e = 0.0f;
-        for (int i = 0; i < NB_BANDS; i++) {
-            float ly = fmaxf(fmaxf(log10f(1e-2f + s_ex[i]), log_max - 7.0f), follow - 1.5f);
-            s_ly[i] = ly;
+#pragma unroll
+        for (int k = 0; k < NB_BANDS; k++) {
+            float ly = fmaxf(fmaxf(__shfl_sync(0xffffffffu, lg, k), log_max - 7.0f), follow - 1.5f);
+            if (i == k) s_ly[k] = ly;
             log_max = fmaxf(log_max, ly);
             follow = fmaxf(follow - 1.5f, ly);
-            e += s_ex[i];
+            e += __shfl_sync(0xffffffffu, exi, k);
         }
-        s_flag = (e < 0.04f) ? 1 : 0;
+        if (i == 0) s_flag = (e < 0.04f) ? 1 : 0;
     }
     __syncthreads();
     const int silent = s_flag;

@@ -145,7 +145,7 @@ __device__ void windowed_rfft(const float* __restrict__ h, int start, const Devi
 // K3: analysis -- X, P, band energies, features (src/features.rs:115-219)
 // ================================================================================================
 __global__ void __launch_bounds__(ST) analysis_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab, int hbase) {
-    __shared__ float2 fa_[480];
+    __shared__ float2 fa_[FREQ_SIZE + 1];  // FFT ping buffer; also receives the 481-bin P spectrum
     __shared__ float2 fb_[480];
     __shared__ float2 xs[FREQ_SIZE + 1];
     __shared__ float cb[NB_BINS_BANDED];

@@ -129,17 +129,35 @@ def test_batch_position_independence_bitwise(builtin_bytes):
 
 
 def test_silence_path_and_recovery(builtin_bytes):
-    """All-zero input: silent frames (vad 0, zero output once the overlap memory drains); state survives."""
+    """Signal -> 45 frames of digital zeros -> signal.  Silent frames: vad exactly 0, state untouched.
+
+    Tolerance note: in the frames right after the cut-off the window holds only the smooth
+    tail of the high-pass filter, so every band above ~1 kHz sits at the f32 rounding floor of the FFT
+    (ex ~ 1e-12 of band 0).  The pitch-correlation features normalise that floor away
+    (exp / sqrt(ex * ep), src/features.rs:136-137), i.e. they are ratios of rounding noise and differ
+    between ANY two f32 FFTs (ours vs the oracle's, and either vs rustfft's) at the 1e-3 level; the GRU
+    remembers it.  Everything that is well-conditioned stays tight: silence flags, pitch (exact), vad."""
     B = 5
     sig = synth_streams(B, 8, seed=11).reshape(B, 8, 480)
     x = np.concatenate([sig, np.zeros((B, 45, 480), np.float32), sig], axis=1)
     ref = oracle_run(builtin_bytes, x)
     b = nb.DenoiseBatch(B)
-    o, v = b.process_host(np.ascontiguousarray(x.transpose(1, 0, 2)))
-    # silent frames: vad exactly 0, output = the (by now ~1e-15) high-pass residue passed straight through
-    assert np.array_equal(v[50], np.zeros(B, np.float32)) and np.abs(o[50]).max() < 1e-6
-    assert np.array_equal(v[50], ref["vad"][:, 50])
-    check_against_oracle(o, v, b.taps()["pitch"], ref, x)
+    outs, vads, pitches, sil = [], [], [], []
+    for t in range(x.shape[1]):
+        o, v = b.process_host(np.ascontiguousarray(x[:, t][None]))
+        outs.append(o[0]); vads.append(v[0])
+        tp = b.taps()
+        pitches.append(tp["pitch"].copy()); sil.append(tp["silence"].copy())
+    o, v = np.stack(outs), np.stack(vads)
+    assert np.array_equal(np.stack(pitches, 1), ref["pitch"])           # integer output: exact, always
+    sil = np.stack(sil, 1)
+    assert sil[:, :8].sum() == 0 and sil[:, 30:53].all() and sil[:, 53:].sum() == 0
+    assert np.array_equal(v[30:53], np.zeros((23, B), np.float32))      # silent frames return vad == 0.0
+    assert np.array_equal(ref["vad"].T[30:53], np.zeros((23, B), np.float32))
+    assert np.abs(o[50]).max() < 1e-6                                    # high-pass residue passed straight through
+    o_ref = ref["out"].transpose(1, 0, 2)
+    assert rel_rms(o[:8], o_ref[:8]) <= OUT_REL_RMS                      # before the cut-off: the usual tolerance
+    assert rel_rms(o, o_ref) <= 2e-3 and np.abs(v - ref["vad"].T).max() <= 2e-3   # after it: see the note above
 
 
 def test_zero_input_from_start():

@@ -22,6 +22,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 # (source, extra flags).  exact.cu is the order-exact pitch path: no FMA contraction.
 UNITS = [
     ("exact.cu", ["-fmad=false"]),
+    ("pitch.cu", ["-fmad=false"]),
     ("spectral.cu", []),
     ("rnn.cu", []),
     ("host.cu", []),

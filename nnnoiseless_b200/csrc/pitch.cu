@@ -1,24 +1,25 @@
-// pitch.cu -- ORDER-EXACT pitch analysis (src/pitch.rs:45-489), 32 streams per thread block.
+// pitch.cu -- ORDER-EXACT pitch analysis (src/pitch.rs:45-489), 16 streams per thread block.
 //
 // Compiled with -fmad=false and written with explicit round-to-nearest intrinsics: every f32 operation
 // is rounded like the reference's scalar code and every sum runs in the reference's order, so the pitch
 // period (an integer) is bit-identical to the reference restatement for every frame.
 //
-// Why 32 streams per block: the pitch path alternates strictly sequential recurrences (5-lag
+// Why many streams per block: the pitch path alternates strictly sequential recurrences (5-lag
 // autocorrelation sums, Levinson, running energies with a clamp per step, best/second-best selection,
 // the k = 2..15 sub-harmonic ladder) with small dense sums (147-lag cross-correlation, ~40 inner
 // products of 480).  With one stream per block the recurrences run on one lane of a warp (measured:
 // 18.6 of 32 lanes active, 25.7k warp-instructions per stream).  Here every recurrence runs
-// LANE-PER-STREAM (32 streams advance in lock-step in one warp, operands fetched as float4 rows of the
+// LANE-PER-STREAM (the block's streams advance in lock-step in one warp, operands fetched as float4 rows of the
 // shared-memory tile), while the dense sums are spread over (stream, lag-group) lane-tasks packed
 // densely into warps and use register sliding windows (one LDS.128 per 16 multiply-adds).
 //
-// Shared-memory tile (dynamic, ~208 KB, one block per SM):
-//   P   [32][868]  2x-decimated, LPC-whitened history (pitch_buf); row stride 868 = 16B aligned and
+// Shared-memory tile (dynamic, SB = 16 streams per block -> ~105 KB, two blocks per SM so that one block's
+// shared-memory-bound inner products overlap the other's FP-bound cross-correlation and serial phases):
+//   P   [SB][868]  2x-decimated, LPC-whitened history (pitch_buf); row stride 868 = 16B aligned and
 //                  = 4 (mod 32) so that lane-per-stream float4 reads are bank-conflict free
-//   Y4  [32][436]  its even samples (the 4x-decimated signal); later reused for the fine running
-//                  energies yn2 [32][297] and then for yy_lookup [32][387]
-//   XC  [32][149]  coarse cross-correlation      YN4 [32][149]  coarse running energy
+//   Y4  [SB][436]  its even samples (the 4x-decimated signal); later reused for the fine running
+//                  energies yn2 [SB][297] and then for yy_lookup [SB][387]
+//   XC  [SB][149]  coarse cross-correlation      YN4 [SB][149]  coarse running energy
 #include "common.cuh"
 
 namespace nnb {
@@ -29,9 +30,10 @@ __device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); 
 __device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
 
-constexpr int SB = 32;    // streams per block
-constexpr int NT = 512;   // threads per block
+constexpr int SB = 16;    // streams per block (lane-per-stream phases use lanes 0..SB-1)
+constexpr int NT = 256;   // threads per block
 constexpr int NW = NT / 32;
+static_assert(SB <= 32 && NW >= 6, "phase-to-warp assignment below assumes >= 6 warps");
 constexpr int PB = PITCH_BUF_SIZE / 2;                                 // 864
 constexpr int MAXP = PITCH_MAX_PERIOD - 3 * PITCH_MIN_PERIOD;          // 588
 constexpr int N4 = PITCH_FRAME_SIZE / 4;                               // 240
@@ -58,12 +60,12 @@ constexpr int OFF_AC = OFF_YN4 + SB * XC_LD;     // [5][32]
 constexpr int OFF_LPC = OFF_AC + 5 * SB;         // [5][32]
 constexpr int OFF_XX = OFF_LPC + 5 * SB;         // [32]
 constexpr int OFF_PG = OFF_XX + SB;              // [32]
-constexpr int OFF_IPR = OFF_PG + SB;             // [32][31]
-constexpr int OFF_FX = OFF_IPR + SB * IPR_LD;    // [32][11]
-constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [5][32]: best4, second4, pitch_idx/t0, t, task counters
-constexpr int SMEM_FLOATS = OFF_SI + 5 * SB;
+constexpr int OFF_IPR = OFF_PG + SB;             // [SB][31]
+constexpr int OFF_FX = OFF_IPR + SB * IPR_LD;    // [SB][11]
+constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [4][SB]: best4, second4, t0, t; then 4 task counters
+constexpr int SMEM_FLOATS = OFF_SI + 4 * SB + 4;
 static_assert(SB * YN2_LD <= SB * Y4_LD && SB * YY_LD <= SB * Y4_LD, "yn2 / yy must fit in the Y4 region");
-static_assert(SMEM_FLOATS * 4 <= 227 * 1024, "shared-memory tile too large");
+static_assert(2 * (SMEM_FLOATS * 4 + 1024) <= 227 * 1024, "two blocks must fit in one SM");
 
 __constant__ int c_second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};  // src/pitch.rs:489
 
@@ -133,9 +135,38 @@ __device__ __forceinline__ float inner_prod_480(const float4* __restrict__ xr, c
     return fa(fa(fa(s0, s1), s2), s3);
 }
 
-__global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict__ hist, int32_t* __restrict__ last_period,
-                                                        float* __restrict__ last_gain, int32_t* __restrict__ pitch_out,
-                                                        int n_streams, int hbase) {
+// Five consecutive lags lag0..lag0+4 of inner_prod(x, y + lag, 480) for one stream with ONE sliding register
+// window over y: acc[c][u] is the reference's accumulator u of lag c (src/pitch.rs:225-244), y read once.
+template <int NLAG>
+__device__ __forceinline__ void inner_prod_window(const float4* __restrict__ xr, const float* __restrict__ y, float* out) {
+    float acc[NLAG][4];
+#pragma unroll
+    for (int c = 0; c < NLAG; c++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[c][u] = 0.0f;
+    float w[8];
+#pragma unroll
+    for (int u = 0; u < 4; u++) w[u] = y[u];
+#pragma unroll 2
+    for (int m = 0; m < HALF_N / 4; m++) {
+        const float4 x = xr[m];
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) w[4 + u] = y[4 * m + 4 + u];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int c = 0; c < NLAG; c++) acc[c][u] = fa(acc[c][u], fm(xv[u], w[u + c]));
+#pragma unroll
+        for (int u = 0; u < 4; u++) w[u] = w[4 + u];
+    }
+#pragma unroll
+    for (int c = 0; c < NLAG; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
+}
+
+__global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ hist, int32_t* __restrict__ last_period,
+                                                      float* __restrict__ last_gain, int32_t* __restrict__ pitch_out,
+                                                      int n_streams, int hbase) {
     extern __shared__ __align__(16) float sm[];
     float* P = sm + OFF_P;
     float* Y4 = sm + OFF_Y4;
@@ -144,46 +175,65 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
     float* AC = sm + OFF_AC;
     float* LPC = sm + OFF_LPC;
     float* XX = sm + OFF_XX;
-    float* PG = sm + OFF_PG;
     float* IPR = sm + OFF_IPR;
     float* FX = sm + OFF_FX;
     int* SI = reinterpret_cast<int*>(sm + OFF_SI);
+    int* CTR = SI + 4 * SB;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ls = lane % SB;  // lane-per-stream phases: lanes >= SB mirror lanes < SB (same reads, same writes)
     const int s0 = blockIdx.x * SB;
     const int ns = min(SB, n_streams - s0);
 
-    // ---- Ph1: pitch_downsample part 1 (src/pitch.rs:455-458); rows of absent streams are zero ----
+    // ---- Ph1: pitch_downsample part 1 (src/pitch.rs:455-458); all 128-bit loads of a row issued before use ----
     for (int r = warp; r < SB; r += NW) {
         float* prow = P + r * P_LD;
+        constexpr int NQ = (PITCH_BUF_SIZE / 4 + 31) / 32;  // 14 float4 per lane
         if (r < ns) {
             const float* h = hist + (size_t)(s0 + r) * HIST_CAP;
-            for (int i = lane; i < PB; i += 32) {
-                int p1 = hbase + 2 * i;
-                int pa = p1 - 1, pb = p1 + 1;
-                if (p1 >= HIST_CAP) p1 -= HIST_CAP;
-                if (pa >= HIST_CAP) pa -= HIST_CAP;
-                if (pb >= HIST_CAP) pb -= HIST_CAP;
-                float v;
-                if (i == 0) v = fm(fa(fm(h[pb], 0.5f), h[p1]), 0.5f);
-                else v = fm(fa(fm(fa(h[pa], h[pb]), 0.5f), h[p1]), 0.5f);
-                prow[i] = v;
+            float4 v[NQ];
+            float pv[NQ];
+#pragma unroll
+            for (int k = 0; k < NQ; k++) {
+                const int m = lane + 32 * k;
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                pv[k] = 0.0f;
+                if (m < PITCH_BUF_SIZE / 4) {
+                    int pos = hbase + 4 * m;  // hbase is a multiple of 4: a float4 never straddles the ring wrap
+                    if (pos >= HIST_CAP) pos -= HIST_CAP;
+                    v[k] = __ldg(reinterpret_cast<const float4*>(h + pos));
+                    if (m > 0) {
+                        int pp = hbase + 4 * m - 1;
+                        if (pp >= HIST_CAP) pp -= HIST_CAP;
+                        pv[k] = __ldg(h + pp);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NQ; k++) {
+                const int m = lane + 32 * k;
+                if (m < PITCH_BUF_SIZE / 4) {
+                    float o0;
+                    if (m == 0) o0 = fm(fa(fm(v[k].y, 0.5f), v[k].x), 0.5f);
+                    else o0 = fm(fa(fm(fa(pv[k], v[k].y), 0.5f), v[k].x), 0.5f);
+                    const float o1 = fm(fa(fm(fa(v[k].y, v[k].w), 0.5f), v[k].z), 0.5f);
+                    *reinterpret_cast<float2*>(prow + 2 * m) = make_float2(o0, o1);
+                }
             }
         } else {
-            for (int i = lane; i < PB; i += 32) prow[i] = 0.0f;
+            for (int i = lane; i < PB; i += 32) prow[i] = 0.0f;  // absent streams: zero rows
         }
         if (lane < 4) {
             prow[PB + lane] = 0.0f;
             Y4[r * Y4_LD + PB / 2 + lane] = 0.0f;
         }
     }
-    if (tid == 0) SI[4 * SB] = 0;  // xcorr task counter
-    if (tid == 1) SI[4 * SB + 1] = 0;
+    if (tid < 4) CTR[tid] = 0;
     __syncthreads();
 
     // ---- Ph2: celt_autocorr, warp k = lag k, lane = stream ----
     if (warp < 5) {
-        const float4* row = reinterpret_cast<const float4*>(P + lane * P_LD);
+        const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
         float v;
         switch (warp) {
             case 0: v = autocorr_lag<0>(row); break;
@@ -192,7 +242,7 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
             case 3: v = autocorr_lag<3>(row); break;
             default: v = autocorr_lag<4>(row); break;
         }
-        AC[warp * SB + lane] = v;
+        AC[warp * SB + ls] = v;
     }
     __syncthreads();
 
@@ -200,7 +250,7 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
     if (warp == 0) {
         float a[5];
 #pragma unroll
-        for (int i = 0; i < 5; i++) a[i] = AC[i * SB + lane];
+        for (int i = 0; i < 5; i++) a[i] = AC[i * SB + ls];
         a[0] = fm(a[0], 1.0001f);
 #pragma unroll
         for (int i = 1; i < 5; i++) {
@@ -237,40 +287,50 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
             tmp = fm(tmp, 0.9f);
             lpc[i] = fm(lpc[i], tmp);
         }
-        LPC[0 * SB + lane] = fa(lpc[0], 0.8f);
-        LPC[1 * SB + lane] = fa(lpc[1], fm(0.8f, lpc[0]));
-        LPC[2 * SB + lane] = fa(lpc[2], fm(0.8f, lpc[1]));
-        LPC[3 * SB + lane] = fa(lpc[3], fm(0.8f, lpc[2]));
-        LPC[4 * SB + lane] = fm(0.8f, lpc[3]);
+        LPC[0 * SB + ls] = fa(lpc[0], 0.8f);
+        LPC[1 * SB + ls] = fa(lpc[1], fm(0.8f, lpc[0]));
+        LPC[2 * SB + ls] = fa(lpc[2], fm(0.8f, lpc[1]));
+        LPC[3 * SB + ls] = fa(lpc[3], fm(0.8f, lpc[2]));
+        LPC[4 * SB + ls] = fm(0.8f, lpc[3]);
     }
     __syncthreads();
 
     // ---- Ph4: fir5_in_place (src/pitch.rs:407-429) + second decimation (src/pitch.rs:74-79).
-    // One warp per row, 32-sample chunks from the END of the row backwards, so the 5 older inputs a chunk
-    // needs are still un-filtered when it is processed. ----
+    // One warp per row, four samples per lane, 128-sample rounds from the END of the row backwards, so the five
+    // older inputs a round needs are still un-filtered when it runs. ----
     for (int r = warp; r < SB; r += NW) {
         float* prow = P + r * P_LD;
-        const float n0 = LPC[0 * SB + r], n1 = LPC[1 * SB + r], n2 = LPC[2 * SB + r], n3 = LPC[3 * SB + r], n4 = LPC[4 * SB + r];
-        for (int c = PB / 32 - 1; c >= 0; c--) {
-            const int i = 32 * c + lane;
-            const float x = prow[i];
-            const float m0 = i >= 1 ? prow[i - 1] : 0.0f;
-            const float m1 = i >= 2 ? prow[i - 2] : 0.0f;
-            const float m2 = i >= 3 ? prow[i - 3] : 0.0f;
-            const float m3 = i >= 4 ? prow[i - 4] : 0.0f;
-            const float m4 = i >= 5 ? prow[i - 5] : 0.0f;
-            const float o = fa(fa(fa(fa(fa(x, fm(n0, m0)), fm(n1, m1)), fm(n2, m2)), fm(n3, m3)), fm(n4, m4));
+        float4* row4 = reinterpret_cast<float4*>(prow);
+        const float nc[5] = {LPC[0 * SB + r], LPC[1 * SB + r], LPC[2 * SB + r], LPC[3 * SB + r], LPC[4 * SB + r]};
+        for (int rd = (PB / 4 + 31) / 32 - 1; rd >= 0; rd--) {
+            const int q = 32 * rd + lane;
+            const bool on = q < PB / 4;
+            float e[9];
+            float o[4];
+            if (on) {
+                const float4 cur = row4[q];
+                const float4 prv = q >= 1 ? row4[q - 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                e[0] = q >= 2 ? prow[4 * q - 5] : 0.0f;
+                e[1] = prv.x; e[2] = prv.y; e[3] = prv.z; e[4] = prv.w;
+                e[5] = cur.x; e[6] = cur.y; e[7] = cur.z; e[8] = cur.w;
+#pragma unroll
+                for (int d = 0; d < 4; d++)
+                    o[d] = fa(fa(fa(fa(fa(e[5 + d], fm(nc[0], e[4 + d])), fm(nc[1], e[3 + d])), fm(nc[2], e[2 + d])), fm(nc[3], e[1 + d])),
+                              fm(nc[4], e[d]));
+            }
             __syncwarp();
-            prow[i] = o;
-            if ((lane & 1) == 0) Y4[r * Y4_LD + (i >> 1)] = o;
+            if (on) {
+                row4[q] = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float2*>(Y4 + r * Y4_LD + 2 * q) = make_float2(o[0], o[2]);
+            }
         }
     }
     __syncthreads();
 
-    // ---- Ph5: coarse xcorr (all warps, dynamic lane-task groups) + coarse running energy (warp 14) + xx (warp 15) ----
+    // ---- Ph5: coarse running energy (warp NW-2) + xx (warp NW-1), then coarse xcorr on all warps ----
     if (warp == NW - 2) {
         // y_sq_norm of find_best_pitch(xcorr, y_lp4, 240) (src/pitch.rs:379-382, 401-402); YN4[i] = value seen at lag i
-        const float4* row = reinterpret_cast<const float4*>(Y4 + lane * Y4_LD);
+        const float4* row = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD);
         float y = 1.0f;
 #pragma unroll 4
         for (int m = 0; m < N4 / 4; m++) {
@@ -280,7 +340,7 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
             y = fa(y, fm(v.z, v.z));
             y = fa(y, fm(v.w, v.w));
         }
-        float* out = YN4 + lane * XC_LD;
+        float* out = YN4 + ls * XC_LD;
         out[0] = y;
 #pragma unroll 2
         for (int m = 0; m < NGRP; m++) {
@@ -294,7 +354,7 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
         }
     } else if (warp == NW - 1) {
         // xx = inner_prod(x, x, 480) with its four interleaved accumulators (src/pitch.rs:133, 225-244)
-        const float4* xr = reinterpret_cast<const float4*>(P + lane * P_LD + HALF_MAX);
+        const float4* xr = reinterpret_cast<const float4*>(P + ls * P_LD + HALF_MAX);
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll 4
         for (int m = 0; m < HALF_N / 4; m++) {
@@ -304,57 +364,73 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
             a2 = fa(a2, fm(x.z, x.z));
             a3 = fa(a3, fm(x.w, x.w));
         }
-        XX[lane] = fa(fa(fa(a0, a1), a2), a3);
+        XX[ls] = fa(fa(fa(a0, a1), a2), a3);
     }
     // coarse xcorr (src/pitch.rs:82, 296-363): lane-task = (stream, group of 4 consecutive lags); every
     // accumulator sums x_lp4[j] * y_lp4[lag + j] with j ascending, operands via a sliding register window.
     for (;;) {
         int T = 0;
-        if (lane == 0) T = atomicAdd(&SI[4 * SB], 1);
+        if (lane == 0) T = atomicAdd(&CTR[0], 1);
         T = __shfl_sync(0xffffffffu, T, 0);
-        if (T >= NGRP) break;
-        const int L = T * 32 + lane;  // 37 * 32 lane-tasks = 32 streams x 37 groups
-        const int s = L / NGRP, g = L - s * NGRP;
-        const float4* xr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + HALF_MAX / 2);
-        const float4* yr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + 4 * g);
-        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
-        float4 w = yr[0];
+        if (T * 32 >= SB * NGRP) break;
+        const int L = T * 32 + lane;
+        if (L < SB * NGRP) {
+            const int s = L / NGRP, g = L - s * NGRP;
+            const float4* xr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + HALF_MAX / 2);
+            const float4* yr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + 4 * g);
+            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+            float4 w = yr[0];
 #pragma unroll 2
-        for (int m = 0; m < N4 / 4; m++) {
-            const float4 x = xr[m];
-            const float4 wn = yr[m + 1];
-            const float e[8] = {w.x, w.y, w.z, w.w, wn.x, wn.y, wn.z, wn.w};
-            const float xv[4] = {x.x, x.y, x.z, x.w};
+            for (int m = 0; m < N4 / 4; m++) {
+                const float4 x = xr[m];
+                const float4 wn = yr[m + 1];
+                const float e[8] = {w.x, w.y, w.z, w.w, wn.x, wn.y, wn.z, wn.w};
+                const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                c0 = fa(c0, fm(xv[u], e[u]));
-                c1 = fa(c1, fm(xv[u], e[u + 1]));
-                c2 = fa(c2, fm(xv[u], e[u + 2]));
-                c3 = fa(c3, fm(xv[u], e[u + 3]));
+                for (int u = 0; u < 4; u++) {
+                    c0 = fa(c0, fm(xv[u], e[u]));
+                    c1 = fa(c1, fm(xv[u], e[u + 1]));
+                    c2 = fa(c2, fm(xv[u], e[u + 2]));
+                    c3 = fa(c3, fm(xv[u], e[u + 3]));
+                }
+                w = wn;
             }
-            w = wn;
+            float* o = XC + s * XC_LD + 4 * g;
+            o[0] = c0;
+            o[1] = c1;
+            o[2] = c2;
+            if (4 * g + 3 < NL4) o[3] = c3;
         }
-        float* o = XC + s * XC_LD + 4 * g;
-        o[0] = c0;
-        o[1] = c1;
-        o[2] = c2;
-        if (4 * g + 3 < NL4) o[3] = c3;
     }
     __syncthreads();
 
-    // ---- Ph6: coarse best/second (warp 0, serial over lags, lane = stream) + fine running energy (warp 1) ----
-    float* YN2 = Y4;  // the 4x-decimated copy is dead from here on
+    // ---- Ph6: warp 0: coarse best/second (serial over lags, lane = stream), then the two 5-lag fine windows of
+    // every stream (src/pitch.rs:83-96).  warp 1: fine running energy.  The 4x-decimated copy is dead: YN2 reuses it.
+    float* YN2 = Y4;
     if (warp == 0) {
         BestTwo b2;
-        const float* xc = XC + lane * XC_LD;
-        const float* yn = YN4 + lane * XC_LD;
+        const float* xc = XC + ls * XC_LD;
+        const float* yn = YN4 + ls * XC_LD;
 #pragma unroll 3
         for (int i = 0; i < NL4; i++) b2.consider(i, xc[i], yn[i]);
-        SI[0 * SB + lane] = b2.best;
-        SI[1 * SB + lane] = b2.second;
+        SI[0 * SB + ls] = b2.best;
+        SI[1 * SB + ls] = b2.second;
+        __syncwarp();
+        // lane-task = (stream, window): lags i0c .. i0c+4, i0c = window start clamped into the valid range; which
+        // of these count as candidates is decided in Ph8 exactly as the reference does (|i - 2 best| <= 2 ...)
+        for (int L = lane; L < 2 * SB; L += 32) {
+            const int s = L >> 1, wdw = L & 1;
+            const int ctr = 2 * SI[wdw * SB + s];
+            const int i0c = min(max(ctr - 2, 0), NL2 - 5);
+            const float* prow = P + s * P_LD;
+            float out[5];
+            inner_prod_window<5>(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + i0c, out);
+#pragma unroll
+            for (int c = 0; c < 5; c++) FX[s * FX_LD + wdw * 5 + c] = fmaxf(out[c], -1.0f);
+        }
     } else if (warp == 1) {
         // y_sq_norm of find_best_pitch(xcorr, y, 480): YN2[i] = value seen at fine lag i
-        const float4* row = reinterpret_cast<const float4*>(P + lane * P_LD);
+        const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
         float y = 1.0f;
 #pragma unroll 4
         for (int m = 0; m < HALF_N / 4; m++) {
@@ -364,7 +440,7 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
             y = fa(y, fm(v.z, v.z));
             y = fa(y, fm(v.w, v.w));
         }
-        float* out = YN2 + lane * YN2_LD;
+        float* out = YN2 + ls * YN2_LD;
         out[0] = y;
 #pragma unroll 2
         for (int m = 0; m < (NL2 + 3) / 4; m++) {
@@ -379,36 +455,23 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
     }
     __syncthreads();
 
-    // ---- Ph7: fine search, 10 candidate lags per stream (src/pitch.rs:88-96); lane-task = (stream, candidate) ----
-    for (int L = tid; L < SB * 10; L += NT) {
-        const int s = L / 10, c = L - s * 10;
-        const int best4 = SI[0 * SB + s], second4 = SI[1 * SB + s];
-        const int i = (c < 5) ? (2 * best4 - 2 + c) : (2 * second4 - 2 + (c - 5));
-        float v = 0.0f;
-        if (i >= 0 && i < NL2) {
-            const float* prow = P + s * P_LD;
-            v = fmaxf(inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + i), -1.0f);
-        }
-        FX[s * FX_LD + c] = v;
-    }
-    __syncthreads();
-
     // ---- Ph8: fine best + pseudo-interpolation (src/pitch.rs:97-114), lane = stream ----
     if (warp == 0) {
-        const int best4 = SI[0 * SB + lane], second4 = SI[1 * SB + lane];
-        const float* fx = FX + lane * FX_LD;
-        const float* yn = YN2 + lane * YN2_LD;
-        const int loA = 2 * best4 - 2, loB = 2 * second4 - 2;
-        // xcorr value at fine lag i: inside either 5-wide window it is the computed value, elsewhere 0
+        const int best4 = SI[0 * SB + ls], second4 = SI[1 * SB + ls];
+        const float* fx = FX + ls * FX_LD;
+        const float* yn = YN2 + ls * YN2_LD;
+        const int cA = 2 * best4, cB = 2 * second4;
+        const int baseA = min(max(cA - 2, 0), NL2 - 5), baseB = min(max(cB - 2, 0), NL2 - 5);
+        // xcorr at fine lag i: computed iff |i - 2 best| <= 2 or |i - 2 second| <= 2 (src/pitch.rs:90-95), else 0
         auto xcf = [&](int i) -> float {
             if (i < 0 || i >= NL2) return 0.0f;
-            if (i >= loA && i <= loA + 4) return fx[i - loA];
-            if (i >= loB && i <= loB + 4) return fx[5 + i - loB];
+            if (abs(i - cA) <= 2) return fx[i - baseA];
+            if (abs(i - cB) <= 2) return fx[5 + i - baseB];
             return 0.0f;
         };
         BestTwo b2;
         // lags outside the windows have xcorr 0 and can never be selected: scan the windows in ascending order
-        const int c0 = min(loA, loB), c1 = max(loA, loB);
+        const int c0 = min(cA, cB) - 2, c1 = max(cA, cB) - 2;
         const int lo0 = max(c0, 0), hi0 = min(c0 + 4, NL2 - 1);
         const int lo1 = max(max(c1, 0), hi0 + 1), hi1 = min(c1 + 4, NL2 - 1);
         for (int i = lo0; i <= hi0; i++) b2.consider(i, xcf(i), yn[i]);
@@ -421,17 +484,17 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
             else if (fs(a, c) > fm(0.7f, fs(b, c))) offset = -1;
         }
         const int pitch_idx = PITCH_MAX_PERIOD - (2 * best - offset);  // src/pitch.rs:49,114
-        SI[2 * SB + lane] = min(pitch_idx / 2, HALF_MAX - 1);          // t0 of remove_doubling
+        SI[2 * SB + ls] = min(pitch_idx / 2, HALF_MAX - 1);             // t0 of remove_doubling
     }
     __syncthreads();
 
-    // ---- Ph9: remove_doubling inner products (src/pitch.rs:134,167-168) + yy_lookup chain (warp 15 first) ----
+    // ---- Ph9: yy_lookup chain (warp NW-1 first) + remove_doubling inner products on all warps ----
     float* YY = Y4;  // yn2 is dead from here on
     if (warp == NW - 1) {
-        // yy_lookup (src/pitch.rs:135-142): stored clamped at 0, carried unclamped; i = 1..384 descending rows
-        const float4* row = reinterpret_cast<const float4*>(P + lane * P_LD);
-        float* out = YY + lane * YY_LD;
-        float y = XX[lane];
+        // yy_lookup (src/pitch.rs:135-142): stored clamped at 0, carried unclamped; i = 1..384 walks the rows downwards
+        const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
+        float* out = YY + ls * YY_LD;
+        float y = XX[ls];
         out[0] = y;
 #pragma unroll 2
         for (int m = 0; m < HALF_MAX / 4; m++) {
@@ -445,48 +508,51 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
             }
         }
     }
-    // lane-task = (stream, q): q = 1: xy(t0); q = 2 + 2(k-2) + {0,1}: t1(k), t1b(k), k = 2..15
+    // lane-task = (stream, q): q = 1: xy(t0); q = 2 + 2(k-2) + {0,1}: t1(k), t1b(k), k = 2..15  (src/pitch.rs:134,167-168)
     for (;;) {
         int T = 0;
-        if (lane == 0) T = atomicAdd(&SI[4 * SB + 1], 1);
+        if (lane == 0) T = atomicAdd(&CTR[1], 1);
         T = __shfl_sync(0xffffffffu, T, 0);
-        if (T >= 29) break;  // 29 * 32 lane-tasks
+        if (T * 32 >= SB * 29) break;
         const int L = T * 32 + lane;
-        const int s = L / 29, q = 1 + (L - s * 29);
-        const int t0 = SI[2 * SB + s];
-        int lagq = -1;
-        if (q == 1) lagq = t0;
-        else {
-            const int k = 2 + ((q - 2) >> 1);
-            const int t1 = (2 * t0 + k) / (2 * k);
-            if (t1 >= MIN_PERIOD2) {
-                if (((q - 2) & 1) == 0) lagq = t1;
-                else if (k == 2) lagq = (t1 + t0 > HALF_MAX) ? t0 : t0 + t1;
-                else lagq = (2 * c_second_check[k] * t0 + k) / (2 * k);
+        if (L < SB * 29) {
+            const int s = L / 29, q = 1 + (L - s * 29);
+            const int t0 = SI[2 * SB + s];
+            int lagq = -1;
+            if (q == 1) lagq = t0;
+            else {
+                const int k = 2 + ((q - 2) >> 1);
+                const int t1 = (2 * t0 + k) / (2 * k);
+                if (t1 >= MIN_PERIOD2) {
+                    if (((q - 2) & 1) == 0) lagq = t1;
+                    else if (k == 2) lagq = (t1 + t0 > HALF_MAX) ? t0 : t0 + t1;
+                    else lagq = (2 * c_second_check[k] * t0 + k) / (2 * k);
+                }
             }
+            float v = 0.0f;
+            if (lagq >= 0) {
+                const float* prow = P + s * P_LD;
+                v = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - lagq);
+            }
+            IPR[s * IPR_LD + q] = v;
         }
-        float v = 0.0f;
-        if (lagq >= 0) {
-            const float* prow = P + s * P_LD;
-            v = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - lagq);
-        }
-        IPR[s * IPR_LD + q] = v;
     }
     __syncthreads();
 
-    // ---- Ph10: the sub-harmonic ladder (src/pitch.rs:144-203), lane = stream ----
+    // ---- Ph10-12: the sub-harmonic ladder (src/pitch.rs:144-203), the +-1 refinement (205-218) and the result,
+    // lane = stream, no further block-level synchronisation ----
     if (warp == 0) {
-        const float* ipr = IPR + lane * IPR_LD;
-        const float* yy = YY + lane * YY_LD;
-        const int t0 = SI[2 * SB + lane];
-        const float xx = XX[lane];
+        const float* ipr = IPR + ls * IPR_LD;
+        const float* yy = YY + ls * YY_LD;
+        const int t0 = SI[2 * SB + ls];
+        const float xx = XX[ls];
         float xy = ipr[1];
         float yyv = yy[t0];
         int prev_period = 0;
         float lg = 0.0f;
-        if (lane < ns) {
-            prev_period = last_period[s0 + lane] / 2;
-            lg = last_gain[s0 + lane];
+        if (ls < ns) {
+            prev_period = last_period[s0 + ls] / 2;
+            lg = last_gain[s0 + ls];
         }
         float best_xy = xy, best_yy = yyv;
         const float g0 = pitch_gain(xy, xx, yyv);
@@ -520,45 +586,39 @@ __global__ void __launch_bounds__(NT, 1) pitch32_kernel(const float* __restrict_
         best_xy = fmaxf(best_xy, 0.0f);
         float pg = (best_yy <= best_xy) ? 1.0f : __fdiv_rn(best_xy, fa(best_yy, 1.0f));
         pg = fminf(pg, g);
-        SI[3 * SB + lane] = t;
-        PG[lane] = pg;
-    }
-    __syncthreads();
 
-    // ---- Ph11: +-1 refinement (src/pitch.rs:205-218): three inner products per stream ----
-    for (int L = tid; L < SB * 3; L += NT) {
-        const int s = L / 3, c = L - s * 3;
-        const int t = SI[3 * SB + s];
-        const float* prow = P + s * P_LD;
-        IPR[s * IPR_LD + c] = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (t + c - 1));
-    }
-    __syncthreads();
-    if (warp == 0 && lane < ns) {
-        const float* ipr = IPR + lane * IPR_LD;
-        const float x_0 = ipr[0], x_1 = ipr[1], x_2 = ipr[2];
-        const int t = SI[3 * SB + lane];
+        // xcorr at lags t-1, t, t+1: one sliding window starting at lag t+1 (lowest address)
+        float xc3[3];
+        const float* prow = P + ls * P_LD;
+        inner_prod_window<3>(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (t + 1), xc3);
+        const float x_0 = xc3[2], x_1 = xc3[1], x_2 = xc3[0];  // window slot c <-> lag t + 1 - c
         int offset = 0;
         if (fs(x_2, x_0) > fm(0.7f, fs(x_1, x_0))) offset = 1;
         else if (fs(x_0, x_2) > fm(0.7f, fs(x_1, x_2))) offset = -1;
         const int tf = max(2 * t + offset, PITCH_MIN_PERIOD);
-        pitch_out[s0 + lane] = tf;
-        last_period[s0 + lane] = tf;
-        last_gain[s0 + lane] = PG[lane];
+        if (lane < ns) {
+            pitch_out[s0 + lane] = tf;
+            last_period[s0 + lane] = tf;
+            last_gain[s0 + lane] = pg;
+        }
     }
 }
 
 }  // namespace
 
 cudaError_t launch_pitch(const BatchBuffers& b, int slot, cudaStream_t st) {
-    static bool attr_set = false;
+    static unsigned long long attr_devs = 0;  // bit d: attribute set on device d
     const size_t smem = sizeof(float) * SMEM_FLOATS;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pitch32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 64 || !((attr_devs >> dev) & 1ull)) {
+        e = cudaFuncSetAttribute(pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev < 64) attr_devs |= 1ull << dev;
     }
     const int grid = (b.n_streams + SB - 1) / SB;
-    pitch32_kernel<<<grid, NT, smem, st>>>(b.hist, b.last_period, b.last_gain, b.pitch, b.n_streams, hist_base(slot));
+    pitch_kernel<<<grid, NT, smem, st>>>(b.hist, b.last_period, b.last_gain, b.pitch, b.n_streams, hist_base(slot));
     return cudaGetLastError();
 }
 

@@ -62,8 +62,9 @@ constexpr int OFF_XX = OFF_LPC + 5 * SB;         // [32]
 constexpr int OFF_PG = OFF_XX + SB;              // [32]
 constexpr int OFF_IPR = OFF_PG + SB;             // [SB][31]
 constexpr int OFF_FX = OFF_IPR + SB * IPR_LD;    // [SB][11]
-constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [4][SB]: best4, second4, t0, t; then 4 task counters
-constexpr int SMEM_FLOATS = OFF_SI + 4 * SB + 4;
+constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [4][SB]: best4, second4, t0, t; then 4 counters
+constexpr int OFF_TASK = OFF_SI + 4 * SB + 4;    // int [SB*29]: compacted remove_doubling inner-product tasks
+constexpr int SMEM_FLOATS = OFF_TASK + SB * 29;
 static_assert(SB * YN2_LD <= SB * Y4_LD && SB * YY_LD <= SB * Y4_LD, "yn2 / yy must fit in the Y4 region");
 static_assert(2 * (SMEM_FLOATS * 4 + 1024) <= 227 * 1024, "two blocks must fit in one SM");
 
@@ -73,28 +74,22 @@ __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
     return __fdiv_rn(xy, __fsqrt_rn(fa(1.0f, fm(xx, yy))));  // src/pitch.rs:485-487
 }
 
-// Selection step of find_best_pitch (src/pitch.rs:383-400).
+// Selection step of find_best_pitch (src/pitch.rs:383-400), written with selects instead of branches (the
+// lanes of a warp are different streams): identical comparisons on identical values.
 struct BestTwo {
     float best_num = -1.0f, second_num = -1.0f, best_den = 0.0f, second_den = 0.0f;
     int best = 0, second = 1;
     __device__ __forceinline__ void consider(int i, float corr, float ysq) {
-        if (corr > 0.0f) {
-            float num = fm(corr, corr);
-            if (fm(num, second_den) > fm(second_num, ysq)) {
-                if (fm(num, best_den) > fm(best_num, ysq)) {
-                    second_num = best_num;
-                    second_den = best_den;
-                    second = best;
-                    best_num = num;
-                    best_den = ysq;
-                    best = i;
-                } else {
-                    second_num = num;
-                    second_den = ysq;
-                    second = i;
-                }
-            }
-        }
+        const float num = fm(corr, corr);
+        const bool c2 = (corr > 0.0f) && (fm(num, second_den) > fm(second_num, ysq));
+        const bool c1 = c2 && (fm(num, best_den) > fm(best_num, ysq));
+        // c1: candidate becomes best, old best becomes second;  c2 && !c1: candidate becomes second
+        second_num = c1 ? best_num : (c2 ? num : second_num);
+        second_den = c1 ? best_den : (c2 ? ysq : second_den);
+        second = c1 ? best : (c2 ? i : second);
+        best_num = c1 ? num : best_num;
+        best_den = c1 ? ysq : best_den;
+        best = c1 ? i : best;
     }
 };
 
@@ -178,7 +173,8 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     float* IPR = sm + OFF_IPR;
     float* FX = sm + OFF_FX;
     int* SI = reinterpret_cast<int*>(sm + OFF_SI);
-    int* CTR = SI + 4 * SB;
+    int* CTR = SI + 4 * SB;  // [0] xcorr task counter, [1] rd task counter, [2] number of rd tasks
+    int* TASK = reinterpret_cast<int*>(sm + OFF_TASK);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ls = lane % SB;  // lane-per-stream phases: lanes >= SB mirror lanes < SB (same reads, same writes)
@@ -404,30 +400,17 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     }
     __syncthreads();
 
-    // ---- Ph6: warp 0: coarse best/second (serial over lags, lane = stream), then the two 5-lag fine windows of
-    // every stream (src/pitch.rs:83-96).  warp 1: fine running energy.  The 4x-decimated copy is dead: YN2 reuses it.
+    // ---- Ph6a: warp 0: coarse best/second (serial over lags, lane = stream; src/pitch.rs:83-84).
+    // warp 1: fine running energy.  The 4x-decimated copy is dead: YN2 reuses it. ----
     float* YN2 = Y4;
     if (warp == 0) {
         BestTwo b2;
         const float* xc = XC + ls * XC_LD;
         const float* yn = YN4 + ls * XC_LD;
-#pragma unroll 3
+#pragma unroll 7
         for (int i = 0; i < NL4; i++) b2.consider(i, xc[i], yn[i]);
         SI[0 * SB + ls] = b2.best;
         SI[1 * SB + ls] = b2.second;
-        __syncwarp();
-        // lane-task = (stream, window): lags i0c .. i0c+4, i0c = window start clamped into the valid range; which
-        // of these count as candidates is decided in Ph8 exactly as the reference does (|i - 2 best| <= 2 ...)
-        for (int L = lane; L < 2 * SB; L += 32) {
-            const int s = L >> 1, wdw = L & 1;
-            const int ctr = 2 * SI[wdw * SB + s];
-            const int i0c = min(max(ctr - 2, 0), NL2 - 5);
-            const float* prow = P + s * P_LD;
-            float out[5];
-            inner_prod_window<5>(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + i0c, out);
-#pragma unroll
-            for (int c = 0; c < 5; c++) FX[s * FX_LD + wdw * 5 + c] = fmaxf(out[c], -1.0f);
-        }
     } else if (warp == 1) {
         // y_sq_norm of find_best_pitch(xcorr, y, 480): YN2[i] = value seen at fine lag i
         const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
@@ -450,6 +433,31 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             for (int d = 0; d < 4; d++) {
                 y = fmaxf(fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d]))), 1.0f);
                 if (4 * m + d + 1 < YN2_LD) out[4 * m + d + 1] = y;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- Ph6b: the two 5-lag fine windows of every stream (src/pitch.rs:88-96), each split into a 3-lag and a
+    // 2-lag sliding window so that two warps share the work.  lane-task = (stream, window): lags i0c .. i0c+4, i0c =
+    // window start clamped into the valid range; which of them count as candidates is decided in Ph8. ----
+    if (warp == 2 || warp == 3) {
+        for (int L = lane; L < 2 * SB; L += 32) {
+            const int s = L >> 1, wdw = L & 1;
+            const int ctr = 2 * SI[wdw * SB + s];
+            const int i0c = min(max(ctr - 2, 0), NL2 - 5);
+            const float* prow = P + s * P_LD;
+            const float4* xr = reinterpret_cast<const float4*>(prow + HALF_MAX);
+            if (warp == 2) {
+                float out[3];
+                inner_prod_window<3>(xr, prow + i0c, out);
+#pragma unroll
+                for (int c = 0; c < 3; c++) FX[s * FX_LD + wdw * 5 + c] = fmaxf(out[c], -1.0f);
+            } else {
+                float out[2];
+                inner_prod_window<2>(xr, prow + i0c + 3, out);
+#pragma unroll
+                for (int c = 0; c < 2; c++) FX[s * FX_LD + wdw * 5 + 3 + c] = fmaxf(out[c], -1.0f);
             }
         }
     }
@@ -484,7 +492,34 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             else if (fs(a, c) > fm(0.7f, fs(b, c))) offset = -1;
         }
         const int pitch_idx = PITCH_MAX_PERIOD - (2 * best - offset);  // src/pitch.rs:49,114
-        SI[2 * SB + ls] = min(pitch_idx / 2, HALF_MAX - 1);             // t0 of remove_doubling
+        const int t0 = min(pitch_idx / 2, HALF_MAX - 1);                // t0 of remove_doubling
+        SI[2 * SB + ls] = t0;
+        // Compact list of the inner products remove_doubling will need (src/pitch.rs:134,152-168): xy(t0), then
+        // for k = 2.. while t1 >= min_period: lags t1 and t1b.  Entry = stream << 16 | q << 10 | lag.
+        int nk = 0;
+        for (int k = 2; k <= 15; k++) {
+            if ((2 * t0 + k) / (2 * k) < MIN_PERIOD2) break;
+            nk++;
+        }
+        const int n = (lane < SB) ? 1 + 2 * nk : 0;
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) CTR[2] = incl;
+        if (lane < SB) {
+            int* tk = TASK + (incl - n);
+            tk[0] = (lane << 16) | (1 << 10) | t0;
+            for (int j = 0; j < nk; j++) {
+                const int k = 2 + j;
+                const int t1 = (2 * t0 + k) / (2 * k);
+                const int t1b = (k == 2) ? ((t1 + t0 > HALF_MAX) ? t0 : t0 + t1) : (2 * c_second_check[k] * t0 + k) / (2 * k);
+                tk[1 + 2 * j] = (lane << 16) | ((2 + 2 * j) << 10) | t1;
+                tk[2 + 2 * j] = (lane << 16) | ((3 + 2 * j) << 10) | t1b;
+            }
+        }
     }
     __syncthreads();
 
@@ -508,33 +543,21 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             }
         }
     }
-    // lane-task = (stream, q): q = 1: xy(t0); q = 2 + 2(k-2) + {0,1}: t1(k), t1b(k), k = 2..15  (src/pitch.rs:134,167-168)
-    for (;;) {
-        int T = 0;
-        if (lane == 0) T = atomicAdd(&CTR[1], 1);
-        T = __shfl_sync(0xffffffffu, T, 0);
-        if (T * 32 >= SB * 29) break;
-        const int L = T * 32 + lane;
-        if (L < SB * 29) {
-            const int s = L / 29, q = 1 + (L - s * 29);
-            const int t0 = SI[2 * SB + s];
-            int lagq = -1;
-            if (q == 1) lagq = t0;
-            else {
-                const int k = 2 + ((q - 2) >> 1);
-                const int t1 = (2 * t0 + k) / (2 * k);
-                if (t1 >= MIN_PERIOD2) {
-                    if (((q - 2) & 1) == 0) lagq = t1;
-                    else if (k == 2) lagq = (t1 + t0 > HALF_MAX) ? t0 : t0 + t1;
-                    else lagq = (2 * c_second_check[k] * t0 + k) / (2 * k);
-                }
-            }
-            float v = 0.0f;
-            if (lagq >= 0) {
+    // lane-task = one entry of the compacted list (stream, q, lag): IPR[stream][q] = inner_prod(x, x - lag, 480)
+    {
+        const int ntask = CTR[2];
+        for (;;) {
+            int T = 0;
+            if (lane == 0) T = atomicAdd(&CTR[1], 1);
+            T = __shfl_sync(0xffffffffu, T, 0);
+            if (T * 32 >= ntask) break;
+            const int L = T * 32 + lane;
+            if (L < ntask) {
+                const int e = TASK[L];
+                const int s = e >> 16, q = (e >> 10) & 63, lagq = e & 1023;
                 const float* prow = P + s * P_LD;
-                v = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - lagq);
+                IPR[s * IPR_LD + q] = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - lagq);
             }
-            IPR[s * IPR_LD + q] = v;
         }
     }
     __syncthreads();

@@ -45,16 +45,18 @@ struct DeviceTables {
     int32_t band_start[NB_BANDS];  // EBAND_5MS[i] << 2
 };
 
-// One dense or GRU layer as laid out on the device (f32-expanded int8 weights).
-//   dense: w[ni][nn], bias[nn]
-//   gru  : wzr[(ni+nn)][2nn]  rows 0..ni-1 = input weights (gates z|r), rows ni.. = recurrent
-//          wh [(ni+nn)][nn]   same for the candidate gate
-//          bias[3nn] (z|r|h)
+// One dense or GRU layer as laid out on the device: int8 weights expanded to f32, output dimension padded
+// to a multiple of 4 (np = (nn + 3) & ~3, padding weights/biases are zero) so that a thread can fetch the
+// weights of 4 adjacent outputs with one 128-bit load.
+//   dense: w[ni][np], bias[np]
+//   gru  : w  = wzr[(ni+nn)][2*np]  rows 0..ni-1 = input weights, rows ni.. = recurrent; columns z | r
+//          wh = wh [(ni+nn)][np]    same for the candidate gate
+//          bias[3*np] (z | r | h)
 struct DeviceLayer {
-    int ni, nn, act;
-    const float* w;     // dense: [ni][nn]; gru: wzr
+    int ni, nn, np, act;
+    const float* w;     // dense: [ni][np]; gru: wzr
     const float* wh;    // gru only
-    const float* bias;  // f32(int8)
+    const float* bias;
 };
 
 struct DeviceModel {

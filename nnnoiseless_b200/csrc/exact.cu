@@ -76,12 +76,15 @@ __global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const float* __re
 }
 
 cudaError_t launch_hp_filter(const BatchBuffers& b, const float* in, long stream_stride, int slot, cudaStream_t st) {
-    static bool attr_set = false;
+    static unsigned long long attr_devs = 0;  // bit d: attribute set on device d
     const size_t smem = sizeof(float) * HP_STREAMS * HP_LD;
-    if (!attr_set) {
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    if (dev >= 64 || !((attr_devs >> dev) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(hp_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev < 64) attr_devs |= 1ull << dev;
     }
     int vec_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (stream_stride % 4 == 0);
     int grid = (b.n_streams + HP_STREAMS - 1) / HP_STREAMS;

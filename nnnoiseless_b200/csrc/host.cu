@@ -106,42 +106,49 @@ struct UploadedModel {
     float* d_blob = nullptr;
 };
 
-size_t dense_floats(const HostDense& l) { return (size_t)l.ni * l.nn + l.nn; }
-size_t gru_floats(const HostGru& l) { return (size_t)(l.ni + l.nn) * 3 * l.nn + 3 * l.nn; }
+inline int pad4(int n) { return (n + 3) & ~3; }
+size_t dense_floats(const HostDense& l) { return (size_t)l.ni * pad4(l.nn) + pad4(l.nn); }
+size_t gru_floats(const HostGru& l) { return (size_t)(l.ni + l.nn) * 3 * pad4(l.nn) + 3 * pad4(l.nn); }
 
 void fill_dense(const HostModel& m, const HostDense& l, std::vector<float>& blob, size_t* off, DeviceLayer* out, float* dbase) {
     const int8_t* w = m.bytes.data() + l.w_off;
     const int8_t* b = m.bytes.data() + l.b_off;
+    const int np = pad4(l.nn);
     out->ni = l.ni;
     out->nn = l.nn;
+    out->np = np;
     out->act = l.act;
     out->w = dbase + *off;
-    for (size_t i = 0; i < (size_t)l.ni * l.nn; i++) blob[(*off)++] = (float)w[i];
+    for (int j = 0; j < l.ni; j++)
+        for (int o = 0; o < np; o++) blob[(*off)++] = o < l.nn ? (float)w[(size_t)j * l.nn + o] : 0.0f;
     out->wh = nullptr;
     out->bias = dbase + *off;
-    for (int i = 0; i < l.nn; i++) blob[(*off)++] = (float)b[i];
+    for (int o = 0; o < np; o++) blob[(*off)++] = o < l.nn ? (float)b[o] : 0.0f;
 }
 
 void fill_gru(const HostModel& m, const HostGru& l, std::vector<float>& blob, size_t* off, DeviceLayer* out, float* dbase) {
     const int8_t* w = m.bytes.data() + l.w_off;
     const int8_t* r = m.bytes.data() + l.r_off;
     const int8_t* b = m.bytes.data() + l.b_off;
-    const int ni = l.ni, nn = l.nn, st = 3 * nn;
+    const int ni = l.ni, nn = l.nn, st = 3 * nn, np = pad4(nn);
     out->ni = ni;
     out->nn = nn;
+    out->np = np;
     out->act = l.act;
-    out->w = dbase + *off;  // wzr [(ni+nn)][2nn]
-    for (int j = 0; j < ni; j++)
-        for (int o = 0; o < 2 * nn; o++) blob[(*off)++] = (float)w[(size_t)j * st + o];
-    for (int j = 0; j < nn; j++)
-        for (int o = 0; o < 2 * nn; o++) blob[(*off)++] = (float)r[(size_t)j * st + o];
-    out->wh = dbase + *off;  // wh [(ni+nn)][nn]
-    for (int j = 0; j < ni; j++)
-        for (int o = 0; o < nn; o++) blob[(*off)++] = (float)w[(size_t)j * st + 2 * nn + o];
-    for (int j = 0; j < nn; j++)
-        for (int o = 0; o < nn; o++) blob[(*off)++] = (float)r[(size_t)j * st + 2 * nn + o];
-    out->bias = dbase + *off;
-    for (int i = 0; i < st; i++) blob[(*off)++] = (float)b[i];
+    auto put_rows = [&](const int8_t* src, int rows, int gate0, int ngates) {
+        for (int j = 0; j < rows; j++)
+            for (int g = 0; g < ngates; g++)
+                for (int o = 0; o < np; o++) blob[(*off)++] = o < nn ? (float)src[(size_t)j * st + (gate0 + g) * nn + o] : 0.0f;
+    };
+    out->w = dbase + *off;  // wzr [(ni+nn)][2np]
+    put_rows(w, ni, 0, 2);
+    put_rows(r, nn, 0, 2);
+    out->wh = dbase + *off;  // wh [(ni+nn)][np]
+    put_rows(w, ni, 2, 1);
+    put_rows(r, nn, 2, 1);
+    out->bias = dbase + *off;  // [3np]
+    for (int g = 0; g < 3; g++)
+        for (int o = 0; o < np; o++) blob[(*off)++] = o < nn ? (float)b[g * nn + o] : 0.0f;
 }
 
 int upload_model(const HostModel& m, UploadedModel* um, cudaStream_t st) {

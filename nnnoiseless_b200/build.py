@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src + ".o")
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            cmd = [NVCC] + ARCH + COMMON + extra + ["-c", s, "-o", o]
+            cmd = [NVCC] + ARCH + COMMON + extra + os.environ.get("NNB_EXTRA_NVCC", "").split() + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             logs.append(r.stderr)
             if r.returncode != 0:

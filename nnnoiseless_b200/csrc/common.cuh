@@ -21,6 +21,7 @@ constexpr int NB_DELTA_CEPS = 6;
 constexpr int NB_FEATURES = 42;
 constexpr int MAX_NEURONS = 128;
 constexpr int NB_BINS_BANDED = 400;  // bins covered by the 21 band segments (EBAND_5MS[21] << 2)
+constexpr int BT_LANES = 96;         // lanes used by the band-sum reduction
 
 // History ring: 4 slots of one frame each.  After frame f is written to slot f % 4 the most
 // recent PITCH_BUF_SIZE samples (the reference's input_mem, src/features.rs:21,97-104) are the
@@ -43,6 +44,13 @@ struct DeviceTables {
     float band_frac[NB_BINS_BANDED];
     int32_t band_of[NB_BINS_BANDED];
     int32_t band_start[NB_BANDS];  // EBAND_5MS[i] << 2
+    // Band sums (src/lib.rs:65-82) as a balanced two-stage reduction: the 800 weighted terms
+    // (band t = frac-part of segment t-1 followed by the (1-frac)-part of segment t) are dealt to
+    // BT_LANES lanes (<= 9 consecutive terms each, all of one band); stage 2 adds each band's lanes.
+    int16_t bt_bin[800];
+    float bt_w[800];
+    int16_t bt_lane_start[BT_LANES + 1];
+    int16_t bt_band_lane[NB_BANDS + 1];
 };
 
 // One dense or GRU layer as laid out on the device: int8 weights expanded to f32, output dimension padded

@@ -98,6 +98,30 @@ void build_tables(DeviceTables* t) {
             t->band_of[idx] = i;
         }
     }
+    // band-sum term table: band b = sum over segment b-1 of frac * c  +  sum over segment b of (1 - frac) * c
+    int nterm = 0, lane = 0;
+    for (int b = 0; b < NB_BANDS; b++) {
+        const int first = nterm;
+        if (b > 0)
+            for (int i = t->band_start[b - 1]; i < t->band_start[b]; i++) {
+                t->bt_bin[nterm] = (int16_t)i;
+                t->bt_w[nterm++] = t->band_frac[i];
+            }
+        if (b < NB_BANDS - 1)
+            for (int i = t->band_start[b]; i < t->band_start[b + 1]; i++) {
+                t->bt_bin[nterm] = (int16_t)i;
+                t->bt_w[nterm++] = 1.0f - t->band_frac[i];
+            }
+        const int n = nterm - first, lanes = (n + 8) / 9;  // <= 9 terms per lane; totals exactly BT_LANES lanes
+        t->bt_band_lane[b] = (int16_t)lane;
+        for (int l = 0; l < lanes; l++) t->bt_lane_start[lane++] = (int16_t)(first + (int)((long)n * l / lanes));
+    }
+    t->bt_band_lane[NB_BANDS] = (int16_t)lane;
+    t->bt_lane_start[lane] = (int16_t)nterm;
+    if (lane != BT_LANES || nterm != 800) {
+        fprintf(stderr, "nnnoiseless_b200: band table construction broken (%d lanes, %d terms)\n", lane, nterm);
+        abort();
+    }
 }
 
 // ---- model upload: int8 -> f32, GRU matrices regrouped per phase (see common.cuh DeviceLayer) ----------

@@ -14,9 +14,19 @@ namespace nnb {
 
 namespace {
 
-constexpr int TS = 32;    // streams per block
-constexpr int RT = 128;   // threads per block
+#ifndef RNN_TS
+#define RNN_TS 32
+#endif
+#ifndef RNN_RT
+#define RNN_RT 128
+#endif
+#ifndef RNN_UNROLL
+#define RNN_UNROLL 4
+#endif
+constexpr int TS = RNN_TS;    // streams per block
+constexpr int RT = RNN_RT;    // threads per block
 constexpr int SG = TS / 4;  // stream groups of 4
+constexpr int UNR = RNN_UNROLL;
 constexpr float WEIGHTS_SCALE = 1.0f / 256.0f;
 
 __device__ __forceinline__ float tansig_approx(float x, const float* __restrict__ table) {
@@ -62,7 +72,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ W, int K, in
         const float4* wp = reinterpret_cast<const float4*>(W) + oq;
         const float4* xp = reinterpret_cast<const float4*>(xin) + sg;
         const int wstride = OP >> 2;
-#pragma unroll 4
+#pragma unroll UNR
         for (int j = 0; j < K; j++) {
             const float4 w = __ldg(wp + (size_t)j * wstride);
             const float4 x = xp[j * (TS / 4)];

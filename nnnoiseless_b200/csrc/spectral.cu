@@ -82,28 +82,46 @@ __device__ void fft480(float2* a, float2* b, const float2* tw) {
     stockham_pass<2, 2, 240>(a, b, tw);
 }
 
-// Band-weighted correlation (src/lib.rs:65-82).  cb[0..400) holds Re(x conj p) per bin.
-// Band t = frac-weighted part of segment t-1 plus (1-frac)-weighted part of segment t.  Four lanes per
-// band (threads 0..87), partial sums combined with shuffles; call with all threads of warps 0-2.
-__device__ void band_sums(const float* cb, const DeviceTables* __restrict__ tab, float* out) {
+// Band-weighted sums (src/lib.rs:65-82), balanced two-stage reduction driven by DeviceTables::bt_*.
+// NS = 3: ex = |X|^2, ep = |P|^2, exp = Re(X conj P) in one sweep (x, p: spectra in shared memory);
+// NS = 1: only |X|^2.  part: shared scratch [NS][BT_LANES].  All threads must call; contains two barriers.
+template <int NS>
+__device__ __forceinline__ void band_sums(const float2* xs, const float2* ps, const DeviceTables* __restrict__ tab, float* part,
+                                          float* o0, float* o1, float* o2) {
     const int tid = threadIdx.x;
-    if (tid < 96) {
-        const int t = tid >> 2, part = tid & 3;
-        float acc = 0.0f;
-        if (t < NB_BANDS) {
-            if (t > 0) {
-                const int lo = tab->band_start[t - 1], hi = tab->band_start[t];
-                for (int i = lo + part; i < hi; i += 4) acc += __ldg(&tab->band_frac[i]) * cb[i];
-            }
-            if (t < NB_BANDS - 1) {
-                const int lo = tab->band_start[t], hi = tab->band_start[t + 1];
-                for (int i = lo + part; i < hi; i += 4) acc += (1.0f - __ldg(&tab->band_frac[i])) * cb[i];
+    if (tid < BT_LANES) {
+        const int t0 = tab->bt_lane_start[tid], t1 = tab->bt_lane_start[tid + 1];
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+        for (int t = t0; t < t1; t++) {
+            const int bin = tab->bt_bin[t];
+            const float w = __ldg(&tab->bt_w[t]);
+            const float2 x = xs[bin];
+            a0 = fmaf(w, x.x * x.x + x.y * x.y, a0);
+            if (NS == 3) {
+                const float2 p = ps[bin];
+                a1 = fmaf(w, p.x * p.x + p.y * p.y, a1);
+                a2 = fmaf(w, x.x * p.x + x.y * p.y, a2);
             }
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (t < NB_BANDS && part == 0) out[t] = (t == 0 || t == NB_BANDS - 1) ? 2.0f * acc : acc;
+        part[tid] = a0;
+        if (NS == 3) {
+            part[BT_LANES + tid] = a1;
+            part[2 * BT_LANES + tid] = a2;
+        }
     }
+    __syncthreads();
+    if (tid < NS * 32) {
+        const int which = tid >> 5, b = tid & 31;
+        if (b < NB_BANDS) {
+            const int l0 = tab->bt_band_lane[b], l1 = tab->bt_band_lane[b + 1];
+            float acc = 0.0f;
+            for (int l = l0; l < l1; l++) acc += part[which * BT_LANES + l];
+            if (b == 0 || b == NB_BANDS - 1) acc *= 2.0f;
+            float* o = which == 0 ? o0 : (which == 1 ? o1 : o2);
+            o[b] = acc;
+        }
+    }
+    __syncthreads();
 }
 
 // interp_band_gain for one bin (src/lib.rs:84-97); bins >= 400 get 0.
@@ -115,28 +133,67 @@ __device__ __forceinline__ float interp_gain(const float* g, const DeviceTables*
 }
 
 // Windowed real FFT of hist[(start + i)], i < 960 (ring-indexed); writes X[0..480] (scaled by wnorm)
-// into xs (shared).  a/b: scratch FFT buffers.  src/features.rs:281-298.
+// into xs (shared, 481 entries).  a/b: scratch FFT buffers.  src/features.rs:281-298.
 __device__ void windowed_rfft(const float* __restrict__ h, int start, const DeviceTables* __restrict__ tab, float2* a,
                               float2* b, float2* xs) {
-    for (int n = threadIdx.x; n < 480; n += ST) {
-        int p0 = start + 2 * n;
-        if (p0 >= HIST_CAP) p0 -= HIST_CAP;
-        int p1 = p0 + 1;
-        if (p1 >= HIST_CAP) p1 -= HIST_CAP;
-        a[n] = make_float2(h[p0] * tab->window[2 * n], h[p1] * tab->window[2 * n + 1]);
+    if ((start & 3) == 0) {
+        // 16-byte aligned window start (always true for lag 0): 128-bit loads; a float4 never straddles the ring wrap
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int q = threadIdx.x + it * ST;
+            if (q < WINDOW_SIZE / 4) {
+                int pos = start + 4 * q;
+                if (pos >= HIST_CAP) pos -= HIST_CAP;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(h + pos));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(tab->window) + q);
+                reinterpret_cast<float4*>(a)[q] = make_float4(v.x * w.x, v.y * w.y, v.z * w.z, v.w * w.w);
+            }
+        }
+    } else {
+        float2 hv[4], wv[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int n = threadIdx.x + it * ST;
+            hv[it] = make_float2(0.f, 0.f);
+            wv[it] = hv[it];
+            if (n < 480) {
+                int p0 = start + 2 * n;
+                if (p0 >= HIST_CAP) p0 -= HIST_CAP;
+                int p1 = p0 + 1;
+                if (p1 >= HIST_CAP) p1 -= HIST_CAP;
+                hv[it] = make_float2(__ldg(h + p0), __ldg(h + p1));
+                wv[it] = __ldg(reinterpret_cast<const float2*>(tab->window) + n);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int n = threadIdx.x + it * ST;
+            if (n < 480) a[n] = make_float2(hv[it].x * wv[it].x, hv[it].y * wv[it].y);
+        }
     }
     __syncthreads();
     fft480(a, b, tab->tw480);
+    // even/odd split, bins k and 480-k together (tw960[480-k] = -conj(tw960[k]))
     const float wn = tab->wnorm;
-    for (int k = threadIdx.x; k <= 480; k += ST) {
-        float2 zk = b[k == 480 ? 0 : k];
-        float2 zc = b[k == 0 ? 0 : 480 - k];
-        float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);
-        float dr = 0.5f * (zk.x - zc.x), di = 0.5f * (zk.y + zc.y);
-        float2 t = cmul(make_float2(di, -dr), tab->tw960[k]);
-        float2 r = make_float2((er + t.x) * wn, (ei + t.y) * wn);
-        if (k == 0 || k == 480) r.y = 0.0f;
-        xs[k] = r;
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int k = threadIdx.x + it * ST;
+        if (k <= 240) {
+            const float2 zk = b[k], zc = b[k == 0 ? 0 : 480 - k];
+            const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);
+            const float dr = 0.5f * (zk.x - zc.x), di = 0.5f * (zk.y + zc.y);
+            const float2 tw = __ldg(&tab->tw960[k]);
+            // bin k: E + (di, -dr) * tw ;  bin 480-k: conj(E) + (di, dr) * (-tw.x, tw.y)
+            const float tx = di * tw.x + dr * tw.y, ty = di * tw.y - dr * tw.x;
+            float2 r0 = make_float2((er + tx) * wn, (ei + ty) * wn);
+            float2 r1 = make_float2((er - tx) * wn, (ty - ei) * wn);
+            if (k == 0) {
+                r0.y = 0.0f;
+                r1.y = 0.0f;
+            }
+            xs[k] = r0;
+            if (k != 240) xs[480 - k] = r1;
+        }
     }
     __syncthreads();
 }
@@ -145,10 +202,11 @@ __device__ void windowed_rfft(const float* __restrict__ h, int start, const Devi
 // K3: analysis -- X, P, band energies, features (src/features.rs:115-219)
 // ================================================================================================
 __global__ void __launch_bounds__(ST) analysis_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab, int hbase) {
-    __shared__ float2 fa_[FREQ_SIZE + 1];  // FFT ping buffer; also receives the 481-bin P spectrum
-    __shared__ float2 fb_[480];
-    __shared__ float2 xs[FREQ_SIZE + 1];
-    __shared__ float cb[NB_BINS_BANDED];
+    __shared__ __align__(16) float2 fa_[480];
+    __shared__ __align__(16) float2 fb_[480];
+    __shared__ __align__(16) float2 xs[FREQ_SIZE + 1];
+    __shared__ __align__(16) float2 ps[FREQ_SIZE + 1];
+    __shared__ float part[3 * BT_LANES];
     __shared__ float s_ex[NB_BANDS], s_ep[NB_BANDS], s_exp[NB_BANDS], s_tmp[NB_BANDS], s_ly[NB_BANDS];
     __shared__ float s_feat[NB_FEATURES];
     __shared__ float s_ceps[CEPS_MEM][NB_BANDS];
@@ -163,30 +221,16 @@ __global__ void __launch_bounds__(ST) analysis_kernel(BatchBuffers bb, const Dev
     int start = hbase + (PITCH_BUF_SIZE - WINDOW_SIZE);
     if (start >= HIST_CAP) start -= HIST_CAP;
     windowed_rfft(h, start, tab, fa_, fb_, xs);
-    float2* Xg = bb.X + (size_t)s * FREQ_SIZE;
-    for (int k = tid; k <= 480; k += ST) Xg[k] = xs[k];
-    for (int k = tid; k < NB_BINS_BANDED; k += ST) cb[k] = xs[k].x * xs[k].x + xs[k].y * xs[k].y;
-    __syncthreads();
-    band_sums(cb, tab, s_ex);
-    __syncthreads();
-
     // ---- P = rfft(window * input_mem[768-pitch .. 1728-pitch]) ----
     start = hbase + (PITCH_BUF_SIZE - WINDOW_SIZE) - pitch;  // >= 0 since pitch <= 768
     if (start >= HIST_CAP) start -= HIST_CAP;
-    float2* ps = fa_;  // P spectrum ends up in fa_ (free once the FFT result sits in fb_)
     windowed_rfft(h, start, tab, fa_, fb_, ps);
+
+    float2* Xg = bb.X + (size_t)s * FREQ_SIZE;
     float2* Pg = bb.P + (size_t)s * NB_BINS_BANDED;
-    for (int k = tid; k < NB_BINS_BANDED; k += ST) {
-        Pg[k] = ps[k];
-        cb[k] = ps[k].x * ps[k].x + ps[k].y * ps[k].y;
-    }
-    __syncthreads();
-    band_sums(cb, tab, s_ep);
-    __syncthreads();
-    for (int k = tid; k < NB_BINS_BANDED; k += ST) cb[k] = xs[k].x * ps[k].x + xs[k].y * ps[k].y;
-    __syncthreads();
-    band_sums(cb, tab, s_exp);
-    __syncthreads();
+    for (int k = tid; k <= 480; k += ST) Xg[k] = xs[k];
+    for (int k = tid; k < NB_BINS_BANDED; k += ST) Pg[k] = ps[k];
+    band_sums<3>(xs, ps, tab, part, s_ex, s_ep, s_exp);
 
     // ---- features ----
     if (tid < NB_BANDS) {
@@ -294,10 +338,10 @@ cudaError_t launch_analysis(const BatchBuffers& b, const DeviceTables* tab, int 
 __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab,
                                                        float* __restrict__ out, long stream_stride,
                                                        float* __restrict__ vad_out) {
-    __shared__ float2 xs[FREQ_SIZE + 1];
-    __shared__ float2 fa_[480];
-    __shared__ float2 fb_[480];
-    __shared__ float cb[NB_BINS_BANDED];
+    __shared__ __align__(16) float2 xs[FREQ_SIZE + 1];
+    __shared__ __align__(16) float2 fa_[480];
+    __shared__ __align__(16) float2 fb_[480];
+    __shared__ float part[BT_LANES];
     __shared__ float s_g[NB_BANDS], s_r[NB_BANDS], s_ne[NB_BANDS], s_ex[NB_BANDS];
 
     const int s = blockIdx.x, tid = threadIdx.x;
@@ -307,6 +351,21 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
 
     if (!silent) {
         const float2* Pg = bb.P + (size_t)s * NB_BINS_BANDED;
+        // per-thread interpolation coordinates of bins tid, tid+128, tid+256, tid+384
+        int bidx[4];
+        float bfr[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int k = tid + it * ST;
+            bidx[it] = k < NB_BINS_BANDED ? tab->band_of[k] : 0;
+            bfr[it] = k < NB_BINS_BANDED ? tab->band_frac[k] : 0.0f;
+        }
+        float2 pv[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int k = tid + it * ST;
+            pv[it] = k < NB_BINS_BANDED ? Pg[k] : make_float2(0.f, 0.f);
+        }
         if (tid < NB_BANDS) {
             // r (src/features.rs:226-235)
             float e = bb.exp[(size_t)s * NB_BANDS + tid], g = bb.gains[(size_t)s * NB_BANDS + tid];
@@ -331,66 +390,92 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
             bb.lastg[(size_t)s * NB_BANDS + tid] = gg;
         }
         __syncthreads();
-        // x += rf * p ; then new band energies
-        for (int k = tid; k < NB_BINS_BANDED; k += ST) {
-            float rf = interp_gain(s_r, tab, k);
-            float2 p = Pg[k];
-            float2 x = xs[k];
-            x.x += p.x * rf;
-            if (k > 0) x.y += p.y * rf;  // bin 0 is the real-valued DC offset
-            xs[k] = x;
-            cb[k] = x.x * x.x + x.y * x.y;
+        // x += rf * p  (bin 0 is the real-valued DC offset; its imaginary part stays 0)
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int k = tid + it * ST;
+            if (k < NB_BINS_BANDED) {
+                const float rf = (1.0f - bfr[it]) * s_r[bidx[it]] + bfr[it] * s_r[bidx[it] + 1];
+                float2 x = xs[k];
+                x.x += pv[it].x * rf;
+                if (k > 0) x.y += pv[it].y * rf;
+                xs[k] = x;
+            }
         }
         __syncthreads();
-        band_sums(cb, tab, s_ne);
-        __syncthreads();
+        band_sums<1>(xs, xs, tab, part, s_ne, s_ne, s_ne);
         if (tid < NB_BANDS) s_r[tid] = sqrtf(s_ex[tid] / (1e-8f + s_ne[tid]));
         __syncthreads();
         // x *= rf2 ; x *= gf   (bins >= 400 are zeroed by both interpolations)
-        for (int k = tid; k <= 480; k += ST) {
-            float m1 = interp_gain(s_r, tab, k);
-            float m2 = interp_gain(s_g, tab, k);
-            float2 x = xs[k];
-            x.x = (x.x * m1) * m2;
-            x.y = (x.y * m1) * m2;
-            xs[k] = x;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int k = tid + it * ST;
+            if (k <= 480) {
+                float2 x = xs[k];
+                if (k < NB_BINS_BANDED) {
+                    const float m1 = (1.0f - bfr[it]) * s_r[bidx[it]] + bfr[it] * s_r[bidx[it] + 1];
+                    const float m2 = (1.0f - bfr[it]) * s_g[bidx[it]] + bfr[it] * s_g[bidx[it] + 1];
+                    x.x = (x.x * m1) * m2;
+                    x.y = (x.y * m1) * m2;
+                } else {
+                    x = make_float2(0.f, 0.f);
+                }
+                xs[k] = x;
+            }
         }
     }
     __syncthreads();
 
-    // ---- inverse real FFT (unnormalised), src/features.rs:263-275 ----
-    for (int k = tid; k < 480; k += ST) {
-        float2 xk = xs[k], xc = xs[480 - k];
-        float xi = (k == 0) ? 0.0f : xk.y;
-        float yi = (k == 0) ? 0.0f : -xc.y;
-        float sr = xk.x + xc.x, si = xi + yi;
-        float dr = xk.x - xc.x, di = xi - yi;
-        float2 w = tab->tw960[k];
-        float2 t = cmul(make_float2(dr, di), make_float2(w.x, -w.y));
-        fa_[k] = make_float2(sr - t.y, -(si + t.x));  // conj(Z)
+    // ---- inverse real FFT (unnormalised), src/features.rs:263-275: Z = 2E + i 2O, fed conjugated to the forward FFT.
+    // Z[k] and Z[480-k] are built together (tw960[480-k] = -conj tw960[k]).
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int k = tid + it * ST;
+        if (k <= 240) {
+            const float2 xk = xs[k], xc = xs[480 - k];
+            const float xi = (k == 0) ? 0.0f : xk.y, yi = (k == 0) ? 0.0f : xc.y;  // DC / Nyquist imaginary parts are ignored
+            const float sr = xk.x + xc.x, si = xi - yi;
+            const float dr = xk.x - xc.x, di = xi + yi;
+            const float2 w = __ldg(&tab->tw960[k]);
+            // t = (dr, di) * conj(w)
+            const float tx = dr * w.x + di * w.y, ty = di * w.x - dr * w.y;
+            fa_[k] = make_float2(sr - ty, -(si + tx));           // conj(Z[k])
+            if (k != 0 && k != 240) {
+                // t' = (-dr, di) * (-w) = (dr w.x + di w.y, dr w.y - di w.x) ; Z[480-k] = (sr - t'.y, -si + t'.x)
+                const float ux = dr * w.x + di * w.y, uy = dr * w.y - di * w.x;
+                fa_[480 - k] = make_float2(sr - uy, -(-si + ux));  // conj(Z[480-k])
+            }
+        }
     }
     __syncthreads();
     fft480(fa_, fb_, tab->tw480);
     float* sm = bb.synth_mem + (size_t)s * FRAME_SIZE;
     float* o = out + (long)s * stream_stride;
-    for (int n = tid; n < 480; n += ST) {
-        // time samples 2n, 2n+1 = (re, -im) of fb_[n]
-        float2 z = fb_[n];
-        float v0 = (z.x * 0.5f) * tab->window[2 * n];
-        float v1 = (-z.y * 0.5f) * tab->window[2 * n + 1];
-        // first half -> output (+ overlap memory); second half -> new overlap memory
-        if (n < 240) {
-            o[2 * n] = v0 + sm[2 * n];
-            o[2 * n + 1] = v1 + sm[2 * n + 1];
+    // time samples 4q..4q+3 = (re, -im) of fb_[2q], fb_[2q+1]; first half -> output (+ overlap memory),
+    // second half -> new overlap memory.  128-bit accesses when the caller's rows are 16-byte aligned.
+    const bool o_vec = ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int q = tid + it * ST;
+        if (q < WINDOW_SIZE / 4) {
+            const float4 z = reinterpret_cast<const float4*>(fb_)[q];
+            const float4 w = __ldg(reinterpret_cast<const float4*>(tab->window) + q);
+            const float4 v = make_float4((z.x * 0.5f) * w.x, (-z.y * 0.5f) * w.y, (z.z * 0.5f) * w.z, (-z.w * 0.5f) * w.w);
+            if (q < FRAME_SIZE / 4) {
+                const float4 m = reinterpret_cast<const float4*>(sm)[q];
+                const float4 r = make_float4(v.x + m.x, v.y + m.y, v.z + m.z, v.w + m.w);
+                if (o_vec) {
+                    reinterpret_cast<float4*>(o)[q] = r;
+                } else {
+                    o[4 * q] = r.x; o[4 * q + 1] = r.y; o[4 * q + 2] = r.z; o[4 * q + 3] = r.w;
+                }
+            } else {
+                reinterpret_cast<float4*>(fa_)[q - FRAME_SIZE / 4] = v;  // staged: sm is still being read by other threads
+            }
         }
-        fa_[n] = make_float2(v0, v1);
     }
     __syncthreads();
-    for (int n = tid; n < 240; n += ST) {
-        float2 v = fa_[240 + n];
-        sm[2 * n] = v.x;
-        sm[2 * n + 1] = v.y;
-    }
+    for (int q = tid; q < FRAME_SIZE / 4; q += ST) reinterpret_cast<float4*>(sm)[q] = reinterpret_cast<const float4*>(fa_)[q];
     if (tid == 0 && vad_out) vad_out[s] = silent ? 0.0f : bb.vad[s];
 }
 

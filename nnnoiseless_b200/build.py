@@ -24,7 +24,8 @@ UNITS = [
     ("exact.cu", ["-fmad=false"]),
     ("pitch.cu", ["-fmad=false"]),
     ("spectral.cu", []),
-    ("rnn.cu", []),
+    ("rnn.cu", ["-DRNN_RT=256", "-DRNN_UNROLL=8"]),
+    ("rnn_mma.cu", []),
     ("host.cu", []),
 ]
 HEADERS = ["common.cuh", "model.hpp", os.path.join("..", "..", "include", "rnnoise.h")]

@@ -72,6 +72,29 @@ struct DeviceModel {
     int state_size;  // vad.nn + noise.nn + denoise.nn
 };
 
+// ---- tensor-core (mma.sync m16n8k16, f16 x f16 -> f32) formulation of the same network -------------------
+// The activations of TS streams live in one shared-memory matrix A[stream][column] (f16 "hi" + f16 "lo" copies:
+// x = hi + lo to ~22 bits); every layer is a product of a column-subset of A with int8 weights (exact in f16),
+// accumulated in f32.  A phase is a list of 16-column chunks of A and the weights pre-packed on the host in
+// mma B-fragment order: wfrag[(chunk * ntiles + tile) * 32 + lane] = {b0, b1} (src/rnn.rs:251-327 semantics).
+constexpr int MMA_MAX_CHUNKS = 28;
+struct MmaPhase {
+    int nchunks;          // K / 16
+    int ntiles;           // output tiles of 8 columns (GRU z|r phase: z tiles then r tiles)
+    const uint2* wfrag;   // [nchunks][ntiles][32]
+    const float* bias;    // [ntiles * 8], zero padded
+    short col[MMA_MAX_CHUNKS];  // first A column of each chunk
+};
+struct DeviceModelMma {
+    MmaPhase dense, vad_zr, vad_h, vad_out, noise_zr, noise_h, den_zr, den_h, out;
+    int nd, nv, nn, ndn;                                   // neurons of dense / vad / noise / denoise
+    int act_dense, act_vad, act_noise, act_den, act_out, act_vadout;
+    int c_feat, c_dense, c_vad, c_noise, c_den, c_rh;      // A column offsets (all multiples of 16)
+    int kp;                                                // A row stride in halves; kp/2 = 4 (mod 8): conflict-free fragment loads
+    int hs;                                                // f32 state row stride (floats)
+    int state_size;
+};
+
 // Per-batch persistent state + per-step intermediates, all [n_streams][...] row-major in HBM.
 struct BatchBuffers {
     int n_streams;
@@ -108,5 +131,7 @@ cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, flo
                              cudaStream_t st);
 // rnn.cu
 cudaError_t launch_rnn(const BatchBuffers& b, const DeviceModel& m, const DeviceTables* tab, cudaStream_t st);
+// rnn_mma.cu
+cudaError_t launch_rnn_mma(const BatchBuffers& b, const DeviceModelMma& m, const DeviceTables* tab, cudaStream_t st);
 
 }  // namespace nnb

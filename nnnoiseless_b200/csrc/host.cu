@@ -10,7 +10,11 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <algorithm>
+#include <utility>
 #include <vector>
+
+#include <cuda_fp16.h>
 
 #include "../../include/rnnoise.h"
 #include "common.cuh"
@@ -193,6 +197,131 @@ int upload_model(const HostModel& m, UploadedModel* um, cudaStream_t st) {
     return 0;
 }
 
+// ---- tensor-core formulation: weights packed in mma.sync m16n8k16 B-fragment order (see common.cuh MmaPhase) ----
+struct UploadedMma {
+    DeviceModelMma dm{};
+    unsigned char* d_blob = nullptr;
+};
+
+struct Seg {
+    int acol, len, recurrent, src_off;  // A column, valid rows, 0 = input matrix / 1 = recurrent matrix, first source row
+};
+
+inline int pad16(int n) { return (n + 15) & ~15; }
+inline uint32_t pack_h2(int a, int b) {
+    return (uint32_t)__half_as_ushort(__float2half((float)a)) | ((uint32_t)__half_as_ushort(__float2half((float)b)) << 16);
+}
+
+struct PhaseBuilder {
+    std::vector<unsigned char> blob;  // host image of the device blob
+    std::vector<std::pair<MmaPhase*, std::pair<size_t, size_t>>> fixups;  // phase, (wfrag offset, bias offset)
+
+    // weight(i_seg_row, out_col) -> int8 value; nout valid outputs per gate; ngates gates laid out as consecutive tile groups
+    template <typename WF, typename BF>
+    void add(MmaPhase* ph, const std::vector<Seg>& segs, int nout, int ngates, WF weight, BF bias) {
+        const int ot = (nout + 7) / 8;
+        ph->ntiles = ngates * ot;
+        ph->nchunks = 0;
+        std::vector<std::pair<int, int>> chunks;  // (segment index, first row in segment)
+        for (size_t si = 0; si < segs.size(); si++)
+            for (int c = 0; c < pad16(segs[si].len); c += 16) {
+                if (ph->nchunks >= MMA_MAX_CHUNKS) abort();
+                ph->col[ph->nchunks++] = (short)(segs[si].acol + c);
+                chunks.push_back({(int)si, c});
+            }
+        while (blob.size() % 16) blob.push_back(0);
+        const size_t woff = blob.size();
+        blob.resize(woff + (size_t)ph->nchunks * ph->ntiles * 32 * sizeof(uint2));
+        uint2* wf = reinterpret_cast<uint2*>(blob.data() + woff);
+        for (int kc = 0; kc < ph->nchunks; kc++) {
+            const Seg& sg = segs[chunks[kc].first];
+            const int r0 = chunks[kc].second;
+            for (int nt = 0; nt < ph->ntiles; nt++) {
+                const int gate = nt / ot, o0 = (nt % ot) * 8;
+                for (int lane = 0; lane < 32; lane++) {
+                    const int g = lane >> 2, t = lane & 3, n = o0 + g;
+                    auto w = [&](int kr) -> int {
+                        const int i = r0 + kr;
+                        if (i >= sg.len || n >= nout) return 0;
+                        return weight(sg, i, gate, n);
+                    };
+                    wf[((size_t)kc * ph->ntiles + nt) * 32 + lane] =
+                        make_uint2(pack_h2(w(2 * t), w(2 * t + 1)), pack_h2(w(2 * t + 8), w(2 * t + 9)));
+                }
+            }
+        }
+        const size_t boff = blob.size();
+        blob.resize(boff + (size_t)ph->ntiles * 8 * sizeof(float));
+        float* bf = reinterpret_cast<float*>(blob.data() + boff);
+        for (int nt = 0; nt < ph->ntiles; nt++)
+            for (int j = 0; j < 8; j++) {
+                const int gate = nt / ot, o = (nt % ot) * 8 + j;
+                bf[nt * 8 + j] = o < nout ? (float)bias(gate, o) : 0.0f;
+            }
+        fixups.push_back({ph, {woff, boff}});
+    }
+};
+
+int upload_model_mma(const HostModel& m, UploadedMma* um, cudaStream_t st) {
+    DeviceModelMma& d = um->dm;
+    const int nd = m.input_dense.nn, nv = m.vad_gru.nn, nn = m.noise_gru.nn, ndn = m.denoise_gru.nn;
+    d.nd = nd; d.nv = nv; d.nn = nn; d.ndn = ndn;
+    d.act_dense = m.input_dense.act; d.act_vad = m.vad_gru.act; d.act_noise = m.noise_gru.act; d.act_den = m.denoise_gru.act;
+    d.act_out = m.denoise_output.act; d.act_vadout = m.vad_output.act;
+    d.c_feat = 0;
+    d.c_dense = pad16(NB_FEATURES);
+    d.c_vad = d.c_dense + pad16(nd);
+    d.c_noise = d.c_vad + pad16(nv);
+    d.c_den = d.c_noise + pad16(nn);
+    d.c_rh = d.c_den + pad16(ndn);
+    int cols = d.c_rh + pad16(std::max(nv, std::max(nn, ndn)));
+    int kp = cols;
+    while ((kp / 2) % 8 != 4) kp += 2;
+    d.kp = kp;
+    int hs = ((nv + 7) & ~7) + ((nn + 7) & ~7) + ((ndn + 7) & ~7);
+    while (hs % 32 != 8) hs++;
+    d.hs = hs;
+    d.state_size = nv + nn + ndn;
+
+    const int8_t* B = m.bytes.data();
+    PhaseBuilder pb;
+    auto dense_w = [&](const HostDense& L) {
+        return [&, B](const Seg& sg, int i, int, int n) -> int { return B[L.w_off + (size_t)(sg.src_off + i) * L.nn + n]; };
+    };
+    auto dense_b = [&](const HostDense& L) { return [&, B](int, int o) -> int { return B[L.b_off + o]; }; };
+    auto gru_w = [&](const HostGru& L, int gate0) {
+        return [&, B, gate0](const Seg& sg, int i, int gate, int n) -> int {
+            const size_t st3 = (size_t)3 * L.nn;
+            const size_t base = sg.recurrent ? L.r_off : L.w_off;
+            return B[base + (size_t)(sg.src_off + i) * st3 + (size_t)(gate0 + gate) * L.nn + n];
+        };
+    };
+    auto gru_b = [&](const HostGru& L, int gate0) { return [&, B, gate0](int gate, int o) -> int { return B[L.b_off + (size_t)(gate0 + gate) * L.nn + o]; }; };
+
+    pb.add(&d.dense, {{d.c_feat, NB_FEATURES, 0, 0}}, nd, 1, dense_w(m.input_dense), dense_b(m.input_dense));
+    pb.add(&d.vad_zr, {{d.c_dense, nd, 0, 0}, {d.c_vad, nv, 1, 0}}, nv, 2, gru_w(m.vad_gru, 0), gru_b(m.vad_gru, 0));
+    pb.add(&d.vad_h, {{d.c_dense, nd, 0, 0}, {d.c_rh, nv, 1, 0}}, nv, 1, gru_w(m.vad_gru, 2), gru_b(m.vad_gru, 2));
+    pb.add(&d.vad_out, {{d.c_vad, nv, 0, 0}}, 1, 1, dense_w(m.vad_output), dense_b(m.vad_output));
+    pb.add(&d.noise_zr, {{d.c_dense, nd, 0, 0}, {d.c_vad, nv, 0, nd}, {d.c_feat, NB_FEATURES, 0, nd + nv}, {d.c_noise, nn, 1, 0}}, nn, 2,
+           gru_w(m.noise_gru, 0), gru_b(m.noise_gru, 0));
+    pb.add(&d.noise_h, {{d.c_dense, nd, 0, 0}, {d.c_vad, nv, 0, nd}, {d.c_feat, NB_FEATURES, 0, nd + nv}, {d.c_rh, nn, 1, 0}}, nn, 1,
+           gru_w(m.noise_gru, 2), gru_b(m.noise_gru, 2));
+    pb.add(&d.den_zr, {{d.c_vad, nv, 0, 0}, {d.c_noise, nn, 0, nv}, {d.c_feat, NB_FEATURES, 0, nv + nn}, {d.c_den, ndn, 1, 0}}, ndn, 2,
+           gru_w(m.denoise_gru, 0), gru_b(m.denoise_gru, 0));
+    pb.add(&d.den_h, {{d.c_vad, nv, 0, 0}, {d.c_noise, nn, 0, nv}, {d.c_feat, NB_FEATURES, 0, nv + nn}, {d.c_rh, ndn, 1, 0}}, ndn, 1,
+           gru_w(m.denoise_gru, 2), gru_b(m.denoise_gru, 2));
+    pb.add(&d.out, {{d.c_den, ndn, 0, 0}}, NB_BANDS, 1, dense_w(m.denoise_output), dense_b(m.denoise_output));
+
+    CK(cudaMalloc(&um->d_blob, pb.blob.size()));
+    for (auto& f : pb.fixups) {
+        f.first->wfrag = reinterpret_cast<const uint2*>(um->d_blob + f.second.first);
+        f.first->bias = reinterpret_cast<const float*>(um->d_blob + f.second.second);
+    }
+    CK(cudaMemcpyAsync(um->d_blob, pb.blob.data(), pb.blob.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 // ---- pcm16 front-end kernels (src/nnnoiseless.rs:147-177, test_data/rnnoise_demo.c:51-55) ---------------
 __global__ void pcm16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,6 +346,8 @@ struct RNNoiseBatch {
     std::vector<void*> allocs;
     DeviceTables* d_tab = nullptr;
     UploadedModel um;
+    UploadedMma umm;
+    bool rnn_fp32 = false;  // NNB_RNN_FP32=1: CUDA-core FP32 GRU kernel instead of the tensor-core one (debug / comparison)
     unsigned long long frame = 0;  // frames processed so far (ring slot = frame % HIST_SLOTS)
     // host-call staging
     float* stage_in = nullptr;
@@ -277,6 +408,12 @@ int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) 
     u.n_streams = n_streams;
     if (upload_model(hm, &b->um, b->stream)) return -1;
     b->allocs.push_back(b->um.d_blob);
+    if (upload_model_mma(hm, &b->umm, b->stream)) return -1;
+    b->allocs.push_back(b->umm.d_blob);
+    {
+        const char* e = getenv("NNB_RNN_FP32");
+        b->rnn_fp32 = e && e[0] == '1';
+    }
     const int SS = b->um.dm.state_size;
     if (dalloc(b, &u.hist, B * HIST_CAP) || dalloc(b, &u.hp_mem, B * 2) || dalloc(b, &u.synth_mem, B * FRAME_SIZE) ||
         dalloc(b, &u.ceps_mem, B * CEPS_MEM * NB_BANDS) || dalloc(b, &u.ceps_id, B) || dalloc(b, &u.last_period, B) ||
@@ -350,7 +487,8 @@ int step(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_s
     if (ev) CK(cudaEventRecord(ev[2], st));
     CK(launch_analysis(b->buf, b->d_tab, slot, st));
     if (ev) CK(cudaEventRecord(ev[3], st));
-    CK(launch_rnn(b->buf, b->um.dm, b->d_tab, st));
+    if (b->rnn_fp32) CK(launch_rnn(b->buf, b->um.dm, b->d_tab, st));
+    else CK(launch_rnn_mma(b->buf, b->umm.dm, b->d_tab, st));
     if (ev) CK(cudaEventRecord(ev[4], st));
     CK(launch_synthesis(b->buf, b->d_tab, out, stream_stride, vad, st));
     if (ev) CK(cudaEventRecord(ev[5], st));

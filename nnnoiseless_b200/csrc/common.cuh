@@ -23,11 +23,15 @@ constexpr int MAX_NEURONS = 128;
 constexpr int NB_BINS_BANDED = 400;  // bins covered by the 21 band segments (EBAND_5MS[21] << 2)
 constexpr int BT_LANES = 96;         // lanes used by the band-sum reduction
 
-// History ring: 4 slots of one frame each.  After frame f is written to slot f % 4 the most
+// History ring: 8 slots of one frame each.  After frame f is written to slot f % 8 the most
 // recent PITCH_BUF_SIZE samples (the reference's input_mem, src/features.rs:21,97-104) are the
-// ring positions (base + i) mod HIST_CAP, i = 0..1727, base = (slot*480 + 672) mod 1920.
-constexpr int HIST_SLOTS = 4;
-constexpr int HIST_CAP = HIST_SLOTS * FRAME_SIZE;  // 1920
+// ring positions (base + i) mod HIST_CAP, i = 0..1727, base = (slot*480 + HIST_CAP - 1248) mod HIST_CAP.
+// (3.6 frames are live; 8 slots let the high-pass kernel of frame f+4 run while frame f is still analysed.)
+constexpr int HIST_SLOTS = 8;
+constexpr int HIST_CAP = HIST_SLOTS * FRAME_SIZE;  // 3840
+// Up to PIPE_DEPTH consecutive frames are in flight at once (each stage on its own CUDA stream); the per-frame
+// intermediates (X, P, band energies, features, pitch, gains, vad) therefore exist in PIPE_DEPTH copies.
+constexpr int PIPE_DEPTH = 4;
 
 __host__ __device__ inline int hist_base(int slot) { return (slot * FRAME_SIZE + (HIST_CAP - (PITCH_BUF_SIZE - FRAME_SIZE))) % HIST_CAP; }
 

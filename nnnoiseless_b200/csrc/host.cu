@@ -338,22 +338,35 @@ __global__ void f32_to_pcm16_kernel(const float* __restrict__ in, short* __restr
 }  // namespace
 
 // ---- the batch handle -----------------------------------------------------------------------------------
+constexpr int kNumKernels = 5;
+const char* const kKernelNames[kNumKernels] = {"hp_filter", "pitch", "analysis", "rnn", "synthesis"};
+constexpr int kEvRing = 16;  // events are recycled after 16 frames (PIPE_DEPTH << 16)
+
 struct RNNoiseBatch {
     int device = 0;
     int n_streams = 0;
-    cudaStream_t stream = nullptr;
-    BatchBuffers buf{};
+    // Frame pipeline: stage i of every frame runs on st[i], so K_i(f) -> K_i(f+1) is stream order; K_{i-1}(f) ->
+    // K_i(f) and the back-pressure K_4(f - PIPE_DEPTH) -> K_0(f) are events.  At small batches one kernel cannot
+    // fill 148 SMs; overlapping the five stages of up to four consecutive frames does.
+    cudaStream_t st[kNumKernels] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t c_in = nullptr, c_out = nullptr;  // host-API copy streams
+    cudaEvent_t ev[kNumKernels][kEvRing];
+    cudaEvent_t ev_in[kEvRing], ev_call = nullptr;
+    bool events_ok = false;
+    BatchBuffers buf{};  // persistent state + set 0 of the intermediates
     std::vector<void*> allocs;
     DeviceTables* d_tab = nullptr;
     UploadedModel um;
     UploadedMma umm;
     bool rnn_fp32 = false;  // NNB_RNN_FP32=1: CUDA-core FP32 GRU kernel instead of the tensor-core one (debug / comparison)
-    unsigned long long frame = 0;  // frames processed so far (ring slot = frame % HIST_SLOTS)
+    bool serial = false;    // NNB_SERIAL=1: all stages on one stream (debug / comparison)
+    unsigned long long frame = 0;  // frames processed so far (ring slot = frame % HIST_SLOTS, set = frame % PIPE_DEPTH)
     // host-call staging
     float* stage_in = nullptr;
     float* stage_out = nullptr;
     float* stage_vad = nullptr;
-    short* stage_pcm = nullptr;
+    short* stage_pcm_in = nullptr;
+    short* stage_pcm_out = nullptr;
     int stage_frames = 0;
     bool stage_has_pcm = false;
 };
@@ -369,26 +382,52 @@ int dalloc(RNNoiseBatch* b, T** p, size_t count) {
     return 0;
 }
 
+// intermediates of frame f live in set f % PIPE_DEPTH
+BatchBuffers view(const RNNoiseBatch* b, unsigned long long f) {
+    BatchBuffers v = b->buf;
+    const size_t k = (size_t)(f % PIPE_DEPTH), B = (size_t)b->n_streams;
+    v.X += k * B * FREQ_SIZE;
+    v.P += k * B * NB_BINS_BANDED;
+    v.ex += k * B * NB_BANDS;
+    v.ep += k * B * NB_BANDS;
+    v.exp += k * B * NB_BANDS;
+    v.features += k * B * NB_FEATURES;
+    v.silence += k * B;
+    v.pitch += k * B;
+    v.gains += k * B * NB_BANDS;
+    v.vad += k * B;
+    return v;
+}
+
+int sync_all(RNNoiseBatch* b) {
+    for (int i = 0; i < kNumKernels; i++) CK(cudaStreamSynchronize(b->st[i]));
+    CK(cudaStreamSynchronize(b->c_in));
+    CK(cudaStreamSynchronize(b->c_out));
+    return 0;
+}
+
 int zero_state(RNNoiseBatch* b) {
-    const size_t B = (size_t)b->n_streams;
+    const size_t B = (size_t)b->n_streams, D = PIPE_DEPTH;
     BatchBuffers& u = b->buf;
     const int SS = b->um.dm.state_size;
-    CK(cudaMemsetAsync(u.hist, 0, B * HIST_CAP * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.hp_mem, 0, B * 2 * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.synth_mem, 0, B * FRAME_SIZE * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.ceps_mem, 0, B * CEPS_MEM * NB_BANDS * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.ceps_id, 0, B * sizeof(int32_t), b->stream));
-    CK(cudaMemsetAsync(u.last_period, 0, B * sizeof(int32_t), b->stream));
-    CK(cudaMemsetAsync(u.last_gain, 0, B * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.gru_state, 0, B * SS * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.lastg, 0, B * NB_BANDS * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.gains, 0, B * NB_BANDS * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.vad, 0, B * sizeof(float), b->stream));
-    CK(cudaMemsetAsync(u.silence, 0, B * sizeof(int32_t), b->stream));
-    CK(cudaMemsetAsync(u.pitch, 0, B * sizeof(int32_t), b->stream));
-    CK(cudaMemsetAsync(u.features, 0, B * NB_FEATURES * sizeof(float), b->stream));
+    if (sync_all(b)) return -1;
+    cudaStream_t s = b->st[0];
+    CK(cudaMemsetAsync(u.hist, 0, B * HIST_CAP * sizeof(float), s));
+    CK(cudaMemsetAsync(u.hp_mem, 0, B * 2 * sizeof(float), s));
+    CK(cudaMemsetAsync(u.synth_mem, 0, B * FRAME_SIZE * sizeof(float), s));
+    CK(cudaMemsetAsync(u.ceps_mem, 0, B * CEPS_MEM * NB_BANDS * sizeof(float), s));
+    CK(cudaMemsetAsync(u.ceps_id, 0, B * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(u.last_period, 0, B * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(u.last_gain, 0, B * sizeof(float), s));
+    CK(cudaMemsetAsync(u.gru_state, 0, B * SS * sizeof(float), s));
+    CK(cudaMemsetAsync(u.lastg, 0, B * NB_BANDS * sizeof(float), s));
+    CK(cudaMemsetAsync(u.gains, 0, D * B * NB_BANDS * sizeof(float), s));
+    CK(cudaMemsetAsync(u.vad, 0, D * B * sizeof(float), s));
+    CK(cudaMemsetAsync(u.silence, 0, D * B * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(u.pitch, 0, D * B * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(u.features, 0, D * B * NB_FEATURES * sizeof(float), s));
     b->frame = 0;
-    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaStreamSynchronize(s));
     return 0;
 }
 
@@ -402,69 +441,95 @@ int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) 
     CK(cudaSetDevice(device));
     b->device = device;
     b->n_streams = n_streams;
-    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    const size_t B = (size_t)n_streams;
+    for (int i = 0; i < kNumKernels; i++) CK(cudaStreamCreateWithFlags(&b->st[i], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->c_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->c_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kNumKernels; i++)
+        for (int k = 0; k < kEvRing; k++) CK(cudaEventCreateWithFlags(&b->ev[i][k], cudaEventDisableTiming));
+    for (int k = 0; k < kEvRing; k++) CK(cudaEventCreateWithFlags(&b->ev_in[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_call, cudaEventDisableTiming));
+    b->events_ok = true;
+    const size_t B = (size_t)n_streams, D = PIPE_DEPTH;
     BatchBuffers& u = b->buf;
     u.n_streams = n_streams;
-    if (upload_model(hm, &b->um, b->stream)) return -1;
+    if (upload_model(hm, &b->um, b->st[0])) return -1;
     b->allocs.push_back(b->um.d_blob);
-    if (upload_model_mma(hm, &b->umm, b->stream)) return -1;
+    if (upload_model_mma(hm, &b->umm, b->st[0])) return -1;
     b->allocs.push_back(b->umm.d_blob);
     {
-        const char* e = getenv("NNB_RNN_FP32");
-        b->rnn_fp32 = e && e[0] == '1';
+        const char* e1 = getenv("NNB_RNN_FP32");
+        b->rnn_fp32 = e1 && e1[0] == '1';
+        const char* e2 = getenv("NNB_SERIAL");
+        b->serial = e2 && e2[0] == '1';
     }
     const int SS = b->um.dm.state_size;
     if (dalloc(b, &u.hist, B * HIST_CAP) || dalloc(b, &u.hp_mem, B * 2) || dalloc(b, &u.synth_mem, B * FRAME_SIZE) ||
         dalloc(b, &u.ceps_mem, B * CEPS_MEM * NB_BANDS) || dalloc(b, &u.ceps_id, B) || dalloc(b, &u.last_period, B) ||
         dalloc(b, &u.last_gain, B) || dalloc(b, &u.gru_state, B * SS) || dalloc(b, &u.lastg, B * NB_BANDS) ||
-        dalloc(b, &u.X, B * FREQ_SIZE) || dalloc(b, &u.P, B * NB_BINS_BANDED) || dalloc(b, &u.ex, B * NB_BANDS) ||
-        dalloc(b, &u.ep, B * NB_BANDS) || dalloc(b, &u.exp, B * NB_BANDS) || dalloc(b, &u.features, B * NB_FEATURES) ||
-        dalloc(b, &u.silence, B) || dalloc(b, &u.pitch, B) || dalloc(b, &u.gains, B * NB_BANDS) || dalloc(b, &u.vad, B) ||
-        dalloc(b, &b->d_tab, 1))
+        dalloc(b, &u.X, D * B * FREQ_SIZE) || dalloc(b, &u.P, D * B * NB_BINS_BANDED) || dalloc(b, &u.ex, D * B * NB_BANDS) ||
+        dalloc(b, &u.ep, D * B * NB_BANDS) || dalloc(b, &u.exp, D * B * NB_BANDS) || dalloc(b, &u.features, D * B * NB_FEATURES) ||
+        dalloc(b, &u.silence, D * B) || dalloc(b, &u.pitch, D * B) || dalloc(b, &u.gains, D * B * NB_BANDS) ||
+        dalloc(b, &u.vad, D * B) || dalloc(b, &b->d_tab, 1))
         return -1;
     DeviceTables* ht = new DeviceTables();
     build_tables(ht);
-    cudaError_t ce = cudaMemcpyAsync(b->d_tab, ht, sizeof(DeviceTables), cudaMemcpyHostToDevice, b->stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
+    cudaError_t ce = cudaMemcpyAsync(b->d_tab, ht, sizeof(DeviceTables), cudaMemcpyHostToDevice, b->st[0]);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->st[0]);
     delete ht;
     if (ce != cudaSuccess) return fail("table upload", ce);
     return zero_state(b);
 }
 
-void batch_release(RNNoiseBatch* b) {
-    if (!b) return;
-    cudaSetDevice(b->device);
-    if (b->stream) cudaStreamSynchronize(b->stream);
-    for (void* p : b->allocs) cudaFree(p);
-    b->allocs.clear();
+void free_stage(RNNoiseBatch* b) {
     if (b->stage_in) cudaFree(b->stage_in);
     if (b->stage_out) cudaFree(b->stage_out);
     if (b->stage_vad) cudaFree(b->stage_vad);
-    if (b->stage_pcm) cudaFree(b->stage_pcm);
+    if (b->stage_pcm_in) cudaFree(b->stage_pcm_in);
+    if (b->stage_pcm_out) cudaFree(b->stage_pcm_out);
     b->stage_in = b->stage_out = b->stage_vad = nullptr;
-    b->stage_pcm = nullptr;
-    if (b->stream) cudaStreamDestroy(b->stream);
-    b->stream = nullptr;
+    b->stage_pcm_in = b->stage_pcm_out = nullptr;
+    b->stage_frames = 0;
+}
+
+void batch_release(RNNoiseBatch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    for (int i = 0; i < kNumKernels; i++)
+        if (b->st[i]) cudaStreamSynchronize(b->st[i]);
+    if (b->c_in) cudaStreamSynchronize(b->c_in);
+    if (b->c_out) cudaStreamSynchronize(b->c_out);
+    for (void* p : b->allocs) cudaFree(p);
+    b->allocs.clear();
+    free_stage(b);
+    if (b->events_ok) {
+        for (int i = 0; i < kNumKernels; i++)
+            for (int k = 0; k < kEvRing; k++) cudaEventDestroy(b->ev[i][k]);
+        for (int k = 0; k < kEvRing; k++) cudaEventDestroy(b->ev_in[k]);
+        cudaEventDestroy(b->ev_call);
+        b->events_ok = false;
+    }
+    for (int i = 0; i < kNumKernels; i++)
+        if (b->st[i]) {
+            cudaStreamDestroy(b->st[i]);
+            b->st[i] = nullptr;
+        }
+    if (b->c_in) cudaStreamDestroy(b->c_in);
+    if (b->c_out) cudaStreamDestroy(b->c_out);
+    b->c_in = b->c_out = nullptr;
 }
 
 int ensure_stage(RNNoiseBatch* b, int n_frames, bool pcm) {
     if (n_frames > b->stage_frames || (pcm && !b->stage_has_pcm)) {
-        CK(cudaStreamSynchronize(b->stream));
+        if (sync_all(b)) return -1;
         const int nf = n_frames > b->stage_frames ? n_frames : b->stage_frames;
-        if (b->stage_in) cudaFree(b->stage_in);
-        if (b->stage_out) cudaFree(b->stage_out);
-        if (b->stage_vad) cudaFree(b->stage_vad);
-        if (b->stage_pcm) cudaFree(b->stage_pcm);
-        b->stage_in = b->stage_out = b->stage_vad = nullptr;
-        b->stage_pcm = nullptr;
-        b->stage_frames = 0;
+        free_stage(b);
         size_t n = (size_t)nf * b->n_streams;
         CK(cudaMalloc(&b->stage_in, n * FRAME_SIZE * sizeof(float)));
         CK(cudaMalloc(&b->stage_out, n * FRAME_SIZE * sizeof(float)));
         CK(cudaMalloc(&b->stage_vad, n * sizeof(float)));
         if (pcm || b->stage_has_pcm) {
-            CK(cudaMalloc(&b->stage_pcm, n * FRAME_SIZE * sizeof(short)));
+            CK(cudaMalloc(&b->stage_pcm_in, n * FRAME_SIZE * sizeof(short)));
+            CK(cudaMalloc(&b->stage_pcm_out, n * FRAME_SIZE * sizeof(short)));
             b->stage_has_pcm = true;
         }
         b->stage_frames = nf;
@@ -472,28 +537,57 @@ int ensure_stage(RNNoiseBatch* b, int n_frames, bool pcm) {
     return 0;
 }
 
-constexpr int kNumKernels = 5;
-const char* const kKernelNames[kNumKernels] = {"hp_filter", "pitch", "analysis", "rnn", "synthesis"};
+int launch_stage(RNNoiseBatch* b, int i, const BatchBuffers& v, float* out, const float* in, float* vad, long stream_stride, int slot,
+                 cudaStream_t s) {
+    switch (i) {
+        case 0: CK(launch_hp_filter(v, in, stream_stride, slot, s)); break;
+        case 1: CK(launch_pitch(v, slot, s)); break;
+        case 2: CK(launch_analysis(v, b->d_tab, slot, s)); break;
+        case 3:
+            if (b->rnn_fp32) CK(launch_rnn(v, b->um.dm, b->d_tab, s));
+            else CK(launch_rnn_mma(v, b->umm.dm, b->d_tab, s));
+            break;
+        default: CK(launch_synthesis(v, b->d_tab, out, stream_stride, vad, s)); break;
+    }
+    return 0;
+}
 
-// One frame for all streams: the five kernels of the path.  ev (optional): kNumKernels + 1 events
-// recorded around the kernels.
-int step(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, cudaStream_t st,
-         cudaEvent_t* ev = nullptr) {
+// One frame for all streams, serialised on ONE stream (profiling, NNB_SERIAL=1).  tev (optional): kNumKernels + 1 timing events.
+int step_serial(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, cudaStream_t s, cudaEvent_t* tev = nullptr) {
     const int slot = (int)(b->frame % HIST_SLOTS);
-    if (ev) CK(cudaEventRecord(ev[0], st));
-    CK(launch_hp_filter(b->buf, in, stream_stride, slot, st));
-    if (ev) CK(cudaEventRecord(ev[1], st));
-    CK(launch_pitch(b->buf, slot, st));
-    if (ev) CK(cudaEventRecord(ev[2], st));
-    CK(launch_analysis(b->buf, b->d_tab, slot, st));
-    if (ev) CK(cudaEventRecord(ev[3], st));
-    if (b->rnn_fp32) CK(launch_rnn(b->buf, b->um.dm, b->d_tab, st));
-    else CK(launch_rnn_mma(b->buf, b->umm.dm, b->d_tab, st));
-    if (ev) CK(cudaEventRecord(ev[4], st));
-    CK(launch_synthesis(b->buf, b->d_tab, out, stream_stride, vad, st));
-    if (ev) CK(cudaEventRecord(ev[5], st));
+    const BatchBuffers v = view(b, b->frame);
+    for (int i = 0; i < kNumKernels; i++) {
+        if (tev) CK(cudaEventRecord(tev[i], s));
+        if (launch_stage(b, i, v, out, in, vad, stream_stride, slot, s)) return -1;
+    }
+    if (tev) CK(cudaEventRecord(tev[kNumKernels], s));
     g_launches.fetch_add(kNumKernels, std::memory_order_relaxed);
     b->frame++;
+    return 0;
+}
+
+// One frame for all streams on the five stage streams.  in_ready (optional): event the first stage must wait for.
+int step_pipelined(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, cudaEvent_t in_ready) {
+    const unsigned long long f = b->frame;
+    const int slot = (int)(f % HIST_SLOTS), e = (int)(f % kEvRing);
+    const BatchBuffers v = view(b, f);
+    if (in_ready) CK(cudaStreamWaitEvent(b->st[0], in_ready, 0));
+    if (f >= (unsigned long long)PIPE_DEPTH) CK(cudaStreamWaitEvent(b->st[0], b->ev[kNumKernels - 1][(int)((f - PIPE_DEPTH) % kEvRing)], 0));
+    for (int i = 0; i < kNumKernels; i++) {
+        if (i > 0) CK(cudaStreamWaitEvent(b->st[i], b->ev[i - 1][e], 0));
+        if (launch_stage(b, i, v, out, in, vad, stream_stride, slot, b->st[i])) return -1;
+        CK(cudaEventRecord(b->ev[i][e], b->st[i]));
+    }
+    g_launches.fetch_add(kNumKernels, std::memory_order_relaxed);
+    b->frame++;
+    return 0;
+}
+
+// Join: make `s` wait for everything issued so far on the stage streams.
+int join_into(RNNoiseBatch* b, cudaStream_t s) {
+    if (b->frame == 0) return 0;
+    // the last synthesis follows every earlier kernel of its frame; earlier frames precede it in stream order per stage
+    CK(cudaStreamWaitEvent(s, b->ev[kNumKernels - 1][(int)((b->frame - 1) % kEvRing)], 0));
     return 0;
 }
 
@@ -580,14 +674,33 @@ int rnnoise_batch_process_device(RNNoiseBatch* b, float* out, const float* in, f
                                  long frame_stride, void* cuda_stream) {
     if (!b || !out || !in) return fail("null argument");
     if (n_frames < 0) return fail("negative n_frames");
+    if (n_frames == 0) return 0;
     CK(cudaSetDevice(b->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+    cudaStream_t us = (cudaStream_t)cuda_stream;
+    if (b->serial) {
+        cudaStream_t s = us ? us : b->st[0];
+        for (int t = 0; t < n_frames; t++)
+            if (step_serial(b, out + (long)t * frame_stride, in + (long)t * frame_stride, vad ? vad + (size_t)t * b->n_streams : nullptr,
+                            stream_stride, s))
+                return -1;
+        if (!us) CK(cudaStreamSynchronize(s));
+        return 0;
+    }
+    cudaEvent_t ready = nullptr;
+    if (us) {  // work queued on the caller's stream (e.g. the producer of `in`) must finish first
+        CK(cudaEventRecord(b->ev_call, us));
+        ready = b->ev_call;
+    }
     for (int t = 0; t < n_frames; t++) {
-        if (step(b, out + (long)t * frame_stride, in + (long)t * frame_stride, vad ? vad + (size_t)t * b->n_streams : nullptr,
-                 stream_stride, st))
+        if (step_pipelined(b, out + (long)t * frame_stride, in + (long)t * frame_stride, vad ? vad + (size_t)t * b->n_streams : nullptr,
+                           stream_stride, t == 0 ? ready : nullptr))
             return -1;
     }
-    if (!cuda_stream) CK(cudaStreamSynchronize(st));
+    if (us) {
+        if (join_into(b, us)) return -1;
+    } else {
+        CK(cudaStreamSynchronize(b->st[kNumKernels - 1]));
+    }
     return 0;
 }
 
@@ -598,10 +711,11 @@ int rnnoise_batch_profile_step(RNNoiseBatch* b, float* out, const float* in, flo
     if (!b || !out || !in || !ms) return fail("null argument");
     if (cap < kNumKernels) return fail("ms[] too small");
     CK(cudaSetDevice(b->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+    if (sync_all(b)) return -1;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->st[0];
     cudaEvent_t ev[kNumKernels + 1];
     for (int i = 0; i <= kNumKernels; i++) CK(cudaEventCreate(&ev[i]));
-    int rc = step(b, out, in, vad, stream_stride, st, ev);
+    int rc = step_serial(b, out, in, vad, stream_stride, st, ev);
     if (rc == 0) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail("profile_step sync", e);
@@ -609,60 +723,82 @@ int rnnoise_batch_profile_step(RNNoiseBatch* b, float* out, const float* in, flo
     if (rc == 0)
         for (int i = 0; i < kNumKernels; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
     for (int i = 0; i <= kNumKernels; i++) cudaEventDestroy(ev[i]);
+    // keep the event bookkeeping of the pipeline consistent: mark this frame's stages complete
+    if (rc == 0) {
+        const int e = (int)((b->frame - 1) % kEvRing);
+        for (int i = 0; i < kNumKernels; i++) cudaEventRecord(b->ev[i][e], st);
+        cudaStreamSynchronize(st);
+    }
     return rc == 0 ? kNumKernels : rc;
+}
+
+// Host buffers: frame t is copied in on c_in, processed on the stage streams, copied out on c_out; copies of
+// neighbouring frames overlap the kernels (true overlap needs page-locked host memory).
+static int process_host_impl(RNNoiseBatch* b, float* out, const float* in, short* out16, const short* in16, float* vad, int n_frames) {
+    const bool pcm = in16 != nullptr;
+    if (ensure_stage(b, n_frames, pcm)) return -1;
+    const size_t B = (size_t)b->n_streams, fs = B * FRAME_SIZE;
+    const int th = 256;
+    const unsigned grid = (unsigned)((fs + th - 1) / th);
+    // everything issued earlier on the stage streams may still be reading/writing the staging buffers
+    if (join_into(b, b->c_in)) return -1;
+    for (int t = 0; t < n_frames; t++) {
+        const int e = (int)(b->frame % kEvRing);
+        if (pcm) {
+            CK(cudaMemcpyAsync(b->stage_pcm_in + t * fs, in16 + t * fs, fs * sizeof(short), cudaMemcpyHostToDevice, b->c_in));
+            pcm16_to_f32_kernel<<<grid, th, 0, b->c_in>>>(b->stage_pcm_in + t * fs, b->stage_in + t * fs, fs);
+            CK(cudaGetLastError());
+        } else {
+            CK(cudaMemcpyAsync(b->stage_in + t * fs, in + t * fs, fs * sizeof(float), cudaMemcpyHostToDevice, b->c_in));
+        }
+        CK(cudaEventRecord(b->ev_in[e], b->c_in));
+        if (b->serial) {
+            CK(cudaStreamWaitEvent(b->st[0], b->ev_in[e], 0));
+            if (step_serial(b, b->stage_out + t * fs, b->stage_in + t * fs, b->stage_vad + (size_t)t * B, FRAME_SIZE, b->st[0])) return -1;
+            CK(cudaEventRecord(b->ev[kNumKernels - 1][e], b->st[0]));
+        } else {
+            if (step_pipelined(b, b->stage_out + t * fs, b->stage_in + t * fs, b->stage_vad + (size_t)t * B, FRAME_SIZE, b->ev_in[e])) return -1;
+        }
+        CK(cudaStreamWaitEvent(b->c_out, b->ev[kNumKernels - 1][e], 0));
+        if (pcm) {
+            f32_to_pcm16_kernel<<<grid, th, 0, b->c_out>>>(b->stage_out + t * fs, b->stage_pcm_out + t * fs, fs);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(out16 + t * fs, b->stage_pcm_out + t * fs, fs * sizeof(short), cudaMemcpyDeviceToHost, b->c_out));
+        } else {
+            CK(cudaMemcpyAsync(out + t * fs, b->stage_out + t * fs, fs * sizeof(float), cudaMemcpyDeviceToHost, b->c_out));
+        }
+        if (vad) CK(cudaMemcpyAsync(vad + (size_t)t * B, b->stage_vad + (size_t)t * B, B * sizeof(float), cudaMemcpyDeviceToHost, b->c_out));
+    }
+    if (pcm) g_launches.fetch_add(2ull * n_frames, std::memory_order_relaxed);
+    CK(cudaStreamSynchronize(b->c_out));
+    CK(cudaStreamSynchronize(b->c_in));
+    return 0;
 }
 
 int rnnoise_batch_process_host(RNNoiseBatch* b, float* out, const float* in, float* vad, int n_frames) {
     if (!b || !out || !in) return fail("null argument");
     if (n_frames <= 0) return n_frames == 0 ? 0 : fail("negative n_frames");
     CK(cudaSetDevice(b->device));
-    if (ensure_stage(b, n_frames, false)) return -1;
-    const size_t n = (size_t)n_frames * b->n_streams;
-    const long fs = (long)b->n_streams * FRAME_SIZE;
-    CK(cudaMemcpyAsync(b->stage_in, in, n * FRAME_SIZE * sizeof(float), cudaMemcpyHostToDevice, b->stream));
-    for (int t = 0; t < n_frames; t++)
-        if (step(b, b->stage_out + t * fs, b->stage_in + t * fs, b->stage_vad + (size_t)t * b->n_streams, FRAME_SIZE, b->stream))
-            return -1;
-    CK(cudaMemcpyAsync(out, b->stage_out, n * FRAME_SIZE * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-    if (vad) CK(cudaMemcpyAsync(vad, b->stage_vad, n * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
-    return 0;
+    return process_host_impl(b, out, in, nullptr, nullptr, vad, n_frames);
 }
 
 int rnnoise_batch_process_pcm16_host(RNNoiseBatch* b, short* out, const short* in, float* vad, int n_frames) {
     if (!b || !out || !in) return fail("null argument");
     if (n_frames <= 0) return n_frames == 0 ? 0 : fail("negative n_frames");
     CK(cudaSetDevice(b->device));
-    if (ensure_stage(b, n_frames, true)) return -1;
-    const size_t n = (size_t)n_frames * b->n_streams;
-    const size_t ns = n * FRAME_SIZE;
-    const long fs = (long)b->n_streams * FRAME_SIZE;
-    const int th = 256;
-    const unsigned grid = (unsigned)((ns + th - 1) / th);
-    CK(cudaMemcpyAsync(b->stage_pcm, in, ns * sizeof(short), cudaMemcpyHostToDevice, b->stream));
-    pcm16_to_f32_kernel<<<grid, th, 0, b->stream>>>(b->stage_pcm, b->stage_in, ns);
-    CK(cudaGetLastError());
-    for (int t = 0; t < n_frames; t++)
-        if (step(b, b->stage_out + t * fs, b->stage_in + t * fs, b->stage_vad + (size_t)t * b->n_streams, FRAME_SIZE, b->stream))
-            return -1;
-    f32_to_pcm16_kernel<<<grid, th, 0, b->stream>>>(b->stage_out, b->stage_pcm, ns);
-    CK(cudaGetLastError());
-    g_launches.fetch_add(2, std::memory_order_relaxed);
-    CK(cudaMemcpyAsync(out, b->stage_pcm, ns * sizeof(short), cudaMemcpyDeviceToHost, b->stream));
-    if (vad) CK(cudaMemcpyAsync(vad, b->stage_vad, n * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
-    return 0;
+    return process_host_impl(b, nullptr, nullptr, out, in, vad, n_frames);
 }
 
 int rnnoise_batch_get_taps(RNNoiseBatch* b, int* pitch, int* silence, float* features, float* gains) {
     if (!b) return fail("null batch");
     CK(cudaSetDevice(b->device));
     const size_t B = (size_t)b->n_streams;
-    CK(cudaStreamSynchronize(b->stream));
-    if (pitch) CK(cudaMemcpy(pitch, b->buf.pitch, B * sizeof(int), cudaMemcpyDeviceToHost));
-    if (silence) CK(cudaMemcpy(silence, b->buf.silence, B * sizeof(int), cudaMemcpyDeviceToHost));
-    if (features) CK(cudaMemcpy(features, b->buf.features, B * NB_FEATURES * sizeof(float), cudaMemcpyDeviceToHost));
-    if (gains) CK(cudaMemcpy(gains, b->buf.lastg, B * NB_BANDS * sizeof(float), cudaMemcpyDeviceToHost));
+    if (sync_all(b)) return -1;
+    const BatchBuffers v = view(b, b->frame ? b->frame - 1 : 0);
+    if (pitch) CK(cudaMemcpy(pitch, v.pitch, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (silence) CK(cudaMemcpy(silence, v.silence, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (features) CK(cudaMemcpy(features, v.features, B * NB_FEATURES * sizeof(float), cudaMemcpyDeviceToHost));
+    if (gains) CK(cudaMemcpy(gains, v.lastg, B * NB_BANDS * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -75,32 +75,44 @@ template <int MAXT>
 __device__ __forceinline__ void run_tiles(const MmaPhase& ph, const __half* Ahi, const __half* Alo, int kp, int lane,
                                           const int (&tiles)[MAXT], int ntl, float (&acc)[MAXT][2][4]) {
     const int g = lane >> 2, t = lane & 3;
-    const uint2* wf = ph.wfrag + lane;
+    const uint2* wp[MAXT];  // this lane's slot in the fragments of tile i; one chunk further = + ntiles * 32
+#pragma unroll
+    for (int i = 0; i < MAXT; i++) wp[i] = ph.wfrag + (size_t)(i < ntl ? tiles[i] : 0) * 32 + lane;
+    const int wstep = ph.ntiles * 32;
     uint2 bn[MAXT];
 #pragma unroll
-    for (int i = 0; i < MAXT; i++) bn[i] = (i < ntl) ? __ldg(wf + (size_t)tiles[i] * 32) : make_uint2(0u, 0u);
-    for (int kc = 0; kc < ph.nchunks; kc++) {
+    for (int i = 0; i < MAXT; i++) bn[i] = (i < ntl) ? __ldg(wp[i]) : make_uint2(0u, 0u);
+    // row bases of this lane's A fragments: rows g and g + 8 of both row tiles, column 2t of the chunk
+    const int rb = g * kp + 2 * t;
+    const __half* ah0 = Ahi + rb;
+    const __half* al0 = Alo + rb;
+    const int r8 = 8 * kp, r16 = 16 * kp;
+    const int nch = ph.nchunks;
+    for (int kc = 0; kc < nch; kc++) {
         uint2 b[MAXT];
 #pragma unroll
         for (int i = 0; i < MAXT; i++) b[i] = bn[i];
-        if (kc + 1 < ph.nchunks) {  // prefetch the next chunk's fragments while this chunk's MMAs run
+        if (kc + 1 < nch) {  // prefetch the next chunk's fragments while this chunk's MMAs run
 #pragma unroll
-            for (int i = 0; i < MAXT; i++)
-                if (i < ntl) bn[i] = __ldg(wf + ((size_t)(kc + 1) * ph.ntiles + tiles[i]) * 32);
+            for (int i = 0; i < MAXT; i++) {
+                wp[i] += wstep;
+                if (i < ntl) bn[i] = __ldg(wp[i]);
+            }
         }
-        const int col = ph.col[kc] + 2 * t;
+        const int col = ph.col[kc];
         uint32_t ah[2][4], al[2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
-            const int r0 = (mt * 16 + g) * kp + col, r1 = r0 + 8 * kp;
-            ah[mt][0] = *reinterpret_cast<const uint32_t*>(Ahi + r0);
-            ah[mt][1] = *reinterpret_cast<const uint32_t*>(Ahi + r1);
-            ah[mt][2] = *reinterpret_cast<const uint32_t*>(Ahi + r0 + 8);
-            ah[mt][3] = *reinterpret_cast<const uint32_t*>(Ahi + r1 + 8);
-            al[mt][0] = *reinterpret_cast<const uint32_t*>(Alo + r0);
-            al[mt][1] = *reinterpret_cast<const uint32_t*>(Alo + r1);
-            al[mt][2] = *reinterpret_cast<const uint32_t*>(Alo + r0 + 8);
-            al[mt][3] = *reinterpret_cast<const uint32_t*>(Alo + r1 + 8);
+            const __half* ph_ = ah0 + col + mt * r16;
+            const __half* pl_ = al0 + col + mt * r16;
+            ah[mt][0] = *reinterpret_cast<const uint32_t*>(ph_);
+            ah[mt][1] = *reinterpret_cast<const uint32_t*>(ph_ + r8);
+            ah[mt][2] = *reinterpret_cast<const uint32_t*>(ph_ + 8);
+            ah[mt][3] = *reinterpret_cast<const uint32_t*>(ph_ + r8 + 8);
+            al[mt][0] = *reinterpret_cast<const uint32_t*>(pl_);
+            al[mt][1] = *reinterpret_cast<const uint32_t*>(pl_ + r8);
+            al[mt][2] = *reinterpret_cast<const uint32_t*>(pl_ + 8);
+            al[mt][3] = *reinterpret_cast<const uint32_t*>(pl_ + r8 + 8);
         }
 #pragma unroll
         for (int i = 0; i < MAXT; i++) {
@@ -236,19 +248,21 @@ __global__ void __launch_bounds__(NT) rnn_mma_kernel(BatchBuffers bb, DeviceMode
         for (int i = tid; i < 201; i += NT) table[i] = tab->tansig[i];
     }
     __syncthreads();
-    for (int i = tid; i < TS * NB_FEATURES; i += NT) {
-        const int s = i / NB_FEATURES, j = i - s * NB_FEATURES;
-        if (s < ns) {
+    {
+        // features [ns][42] and GRU state [ns][SS] of this block are contiguous in HBM: fetch them with 128-bit loads,
+        // all requests of a thread in flight before the first use (full blocks with 16-byte aligned bases)
+        const float* fsrc = bb.features + (size_t)s0 * NB_FEATURES;
+        const float* ssrc = bb.gru_state + (size_t)s0 * SS;
+        const bool vec = ns == TS && ((reinterpret_cast<uintptr_t>(fsrc) | reinterpret_cast<uintptr_t>(ssrc)) & 15) == 0 && (SS & 3) == 0;
+        auto put_feat = [&](int e, float v) {
+            const int s = e / NB_FEATURES, j = e - s * NB_FEATURES;
             __half hi, lo;
-            split_f16(bb.features[(size_t)(s0 + s) * NB_FEATURES + j], hi, lo);
+            split_f16(v, hi, lo);
             Ahi[s * kp + m.c_feat + j] = hi;
             Alo[s * kp + m.c_feat + j] = lo;
-        }
-    }
-    for (int i = tid; i < TS * SS; i += NT) {
-        const int s = i / SS, j = i - s * SS;
-        if (s < ns) {
-            const float v = bb.gru_state[(size_t)(s0 + s) * SS + j];
+        };
+        auto put_state = [&](int e, float v) {
+            const int s = e / SS, j = e - s * SS;
             int ac, ho;
             if (j < m.nv) { ac = m.c_vad + j; ho = so_v + j; }
             else if (j < m.nv + m.nn) { ac = m.c_noise + (j - m.nv); ho = so_n + (j - m.nv); }
@@ -258,6 +272,48 @@ __global__ void __launch_bounds__(NT) rnn_mma_kernel(BatchBuffers bb, DeviceMode
             split_f16(v, hi, lo);
             Ahi[s * kp + ac] = hi;
             Alo[s * kp + ac] = lo;
+        };
+        if (vec) {
+            constexpr int NF4 = TS * NB_FEATURES / 4;          // 336
+            constexpr int FQ = (NF4 + NT - 1) / NT;            // 3 per thread
+            float4 fv[FQ];
+#pragma unroll
+            for (int k = 0; k < FQ; k++) {
+                const int q = tid + k * NT;
+                fv[k] = q < NF4 ? __ldg(reinterpret_cast<const float4*>(fsrc) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const int ns4 = TS * SS / 4;
+            for (int q0 = 0; q0 < ns4; q0 += 8 * NT) {
+                float4 sv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int q = q0 + tid + k * NT;
+                    sv[k] = q < ns4 ? __ldg(reinterpret_cast<const float4*>(ssrc) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int q = q0 + tid + k * NT;
+                    if (q < ns4) {
+                        put_state(4 * q, sv[k].x);
+                        put_state(4 * q + 1, sv[k].y);
+                        put_state(4 * q + 2, sv[k].z);
+                        put_state(4 * q + 3, sv[k].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < FQ; k++) {
+                const int q = tid + k * NT;
+                if (q < NF4) {
+                    put_feat(4 * q, fv[k].x);
+                    put_feat(4 * q + 1, fv[k].y);
+                    put_feat(4 * q + 2, fv[k].z);
+                    put_feat(4 * q + 3, fv[k].w);
+                }
+            }
+        } else {
+            for (int i = tid; i < ns * NB_FEATURES; i += NT) put_feat(i, fsrc[i]);
+            for (int i = tid; i < ns * SS; i += NT) put_state(i, ssrc[i]);
         }
     }
     __syncthreads();

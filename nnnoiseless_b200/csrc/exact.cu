@@ -19,12 +19,12 @@ __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); 
 // K1: high-pass biquad, one lane per stream (src/util.rs:95-107: f64 arithmetic, f32 state, 480 dependent
 // steps per frame).  The recurrence cannot be re-associated, so throughput comes from running many of them
 // side by side: 128 streams per block (one per thread), four blocks per SM.  The [128][480] input is streamed
-// in five 96-sample chunks staged through shared memory, so global traffic is coalesced 128-bit while each
-// lane walks its own row (stride 97 words: conflict-free).
+// in six 80-sample chunks staged through shared memory, so global traffic is coalesced 128-bit while each
+// lane walks its own row (stride 81 words: conflict-free).
 // ================================================================================================
 constexpr int HP_STREAMS = 128;
 constexpr int HP_THREADS = 128;
-constexpr int HP_CHUNK = 96;
+constexpr int HP_CHUNK = 80;
 constexpr int HP_LD = HP_CHUNK + 1;
 static_assert(FRAME_SIZE % HP_CHUNK == 0 && HP_CHUNK % 4 == 0, "chunking must tile the frame");
 
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const float* __re
             }
         }
         __syncthreads();
-        // hist rows are 16-byte aligned (HIST_CAP*4, slot*480*4 and c*96*4 are multiples of 16)
+        // hist rows are 16-byte aligned (HIST_CAP*4, slot*480*4 and c*80*4 are multiples of 16)
         for (int idx = tid; idx < ns * Q; idx += HP_THREADS) {
             const int row = idx / Q, q = idx - row * Q;
             const float* t = tile + row * HP_LD + 4 * q;

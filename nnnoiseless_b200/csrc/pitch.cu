@@ -30,10 +30,17 @@ __device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); 
 __device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
 
-constexpr int SB = 16;    // streams per block (lane-per-stream phases use lanes 0..SB-1)
-constexpr int NT = 256;   // threads per block
+#ifndef PITCH_SB
+#define PITCH_SB 16
+#endif
+#ifndef PITCH_NT
+#define PITCH_NT 256
+#endif
+constexpr int SB = PITCH_SB;    // streams per block (lane-per-stream phases use lanes 0..SB-1, mirrored on the others)
+constexpr int NT = PITCH_NT;    // threads per block
 constexpr int NW = NT / 32;
-static_assert(SB <= 32 && NW >= 6, "phase-to-warp assignment below assumes >= 6 warps");
+constexpr int BLOCKS_PER_SM = (227 * 1024) / ((SB * (868 + 436 + 2 * 149 + 31 + 11 + 29) + 64 * SB + 64) * 4 + 1024);
+static_assert(SB <= 32 && (32 % SB) == 0 && NW >= 4, "phase-to-warp assignment below assumes >= 4 warps");
 constexpr int PB = PITCH_BUF_SIZE / 2;                                 // 864
 constexpr int MAXP = PITCH_MAX_PERIOD - 3 * PITCH_MIN_PERIOD;          // 588
 constexpr int N4 = PITCH_FRAME_SIZE / 4;                               // 240
@@ -66,7 +73,7 @@ constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [4][SB]: best4, second4,
 constexpr int OFF_TASK = OFF_SI + 4 * SB + 4;    // int [SB*29]: compacted remove_doubling inner-product tasks
 constexpr int SMEM_FLOATS = OFF_TASK + SB * 29;
 static_assert(SB * YN2_LD <= SB * Y4_LD && SB * YY_LD <= SB * Y4_LD, "yn2 / yy must fit in the Y4 region");
-static_assert(2 * (SMEM_FLOATS * 4 + 1024) <= 227 * 1024, "two blocks must fit in one SM");
+static_assert(SMEM_FLOATS * 4 + 1024 <= 227 * 1024, "tile must fit in one SM");
 
 __constant__ int c_second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};  // src/pitch.rs:489
 
@@ -159,7 +166,21 @@ __device__ __forceinline__ void inner_prod_window(const float4* __restrict__ xr,
     for (int c = 0; c < NLAG; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
 }
 
-__global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ hist, int32_t* __restrict__ last_period,
+#ifdef PITCH_PROFILE
+__device__ unsigned long long g_pitch_prof[16];
+#define PPROF(k)                                                                  \
+    do {                                                                          \
+        if (threadIdx.x == 0) {                                                   \
+            const long long now_ = clock64();                                     \
+            atomicAdd(&g_pitch_prof[k], (unsigned long long)(now_ - pprof_t_));   \
+            pprof_t_ = now_;                                                      \
+        }                                                                         \
+    } while (0)
+#else
+#define PPROF(k)
+#endif
+
+__global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_SM : 512 / NT) pitch_kernel(const float* __restrict__ hist, int32_t* __restrict__ last_period,
                                                       float* __restrict__ last_gain, int32_t* __restrict__ pitch_out,
                                                       int n_streams, int hbase) {
     extern __shared__ __align__(16) float sm[];
@@ -180,6 +201,9 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     const int ls = lane % SB;  // lane-per-stream phases: lanes >= SB mirror lanes < SB (same reads, same writes)
     const int s0 = blockIdx.x * SB;
     const int ns = min(SB, n_streams - s0);
+#ifdef PITCH_PROFILE
+    long long pprof_t_ = clock64();
+#endif
 
     // ---- Ph1: pitch_downsample part 1 (src/pitch.rs:455-458); all 128-bit loads of a row issued before use ----
     for (int r = warp; r < SB; r += NW) {
@@ -226,21 +250,23 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     }
     if (tid < 4) CTR[tid] = 0;
     __syncthreads();
+    PPROF(0);
 
     // ---- Ph2: celt_autocorr, warp k = lag k, lane = stream ----
-    if (warp < 5) {
+    for (int k = warp; k < 5; k += NW) {
         const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
         float v;
-        switch (warp) {
+        switch (k) {
             case 0: v = autocorr_lag<0>(row); break;
             case 1: v = autocorr_lag<1>(row); break;
             case 2: v = autocorr_lag<2>(row); break;
             case 3: v = autocorr_lag<3>(row); break;
             default: v = autocorr_lag<4>(row); break;
         }
-        AC[warp * SB + ls] = v;
+        AC[k * SB + ls] = v;
     }
     __syncthreads();
+    PPROF(1);
 
     // ---- Ph3: noise floor, lag window, LPC(4), bandwidth expansion, extra zero (src/pitch.rs:462-480, 257-292) ----
     if (warp == 0) {
@@ -290,6 +316,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         LPC[4 * SB + ls] = fm(0.8f, lpc[3]);
     }
     __syncthreads();
+    PPROF(2);
 
     // ---- Ph4: fir5_in_place (src/pitch.rs:407-429) + second decimation (src/pitch.rs:74-79).
     // One warp per row, four samples per lane, 128-sample rounds from the END of the row backwards, so the five
@@ -322,6 +349,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
+    PPROF(3);
 
     // ---- Ph5: coarse running energy (warp NW-2) + xx (warp NW-1), then coarse xcorr on all warps ----
     if (warp == NW - 2) {
@@ -399,6 +427,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
+    PPROF(4);
 
     // ---- Ph6a: warp 0: coarse best/second (serial over lags, lane = stream; src/pitch.rs:83-84).
     // warp 1: fine running energy.  The 4x-decimated copy is dead: YN2 reuses it. ----
@@ -437,6 +466,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
+    PPROF(5);
 
     // ---- Ph6b: the two 5-lag fine windows of every stream (src/pitch.rs:88-96), each split into a 3-lag and a
     // 2-lag sliding window so that two warps share the work.  lane-task = (stream, window): lags i0c .. i0c+4, i0c =
@@ -462,6 +492,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
+    PPROF(6);
 
     // ---- Ph8: fine best + pseudo-interpolation (src/pitch.rs:97-114), lane = stream ----
     if (warp == 0) {
@@ -522,6 +553,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
+    PPROF(7);
 
     // ---- Ph9: yy_lookup chain (warp NW-1 first) + remove_doubling inner products on all warps ----
     float* YY = Y4;  // yn2 is dead from here on
@@ -561,6 +593,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
+    PPROF(8);
 
     // ---- Ph10-12: the sub-harmonic ladder (src/pitch.rs:144-203), the +-1 refinement (205-218) and the result,
     // lane = stream, no further block-level synchronisation ----
@@ -625,9 +658,21 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             last_gain[s0 + lane] = pg;
         }
     }
+    PPROF(9);
 }
 
 }  // namespace
+
+#ifdef PITCH_PROFILE
+extern "C" void nnb_pitch_prof_read(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_pitch_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_pitch_prof, z, sizeof z);
+    }
+}
+#endif
 
 cudaError_t launch_pitch(const BatchBuffers& b, int slot, cudaStream_t st) {
     static unsigned long long attr_devs = 0;  // bit d: attribute set on device d

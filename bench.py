@@ -125,9 +125,19 @@ def synth_on_device(torch, B, T, device, seed):
     return x
 
 
-def cpu_baseline_run(x_bt, threads=0):
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arm must not obey that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline_run(x_bt, threads=None):
     """Times the oracle (C restatement of the reference) on [n][T][480] host samples; returns frames/s, threads."""
     import oracle
+    if threads is None:
+        threads = host_threads()
     import nnnoiseless_b200 as nb
     with open(nb.BUILTIN_WEIGHTS_PATH, "rb") as f:
         m = oracle.Model(f.read())
@@ -140,7 +150,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     T = args.frames
     n = min(args.streams, max(cores * 8, 8))
     from nnnoiseless_b200.synth import synth_streams  # numpy generator, same signal family as the GPU arm
@@ -299,7 +309,7 @@ def run_b200(args):
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample of the same workload ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = host_threads()
         n = min(B, max(8, 16 * cores))
         xs = x[:, :n].permute(1, 0, 2).contiguous().cpu().numpy()  # [n][T][480]
         cpu_baseline_run(xs[: max(1, min(n, cores))])  # warm-up (tables, page faults)

@@ -82,6 +82,46 @@ __device__ void fft480(float2* a, float2* b, const float2* tw) {
     stockham_pass<2, 2, 240>(a, b, tw);
 }
 
+// Two independent 480-point FFTs advanced together (same indices, same twiddles, half the barriers).
+template <int R, int N, int S>
+__device__ __forceinline__ void stockham_pass2(const float2* __restrict__ x0, float2* __restrict__ y0, const float2* __restrict__ x1,
+                                               float2* __restrict__ y1, const float2* __restrict__ tw) {
+    constexpr int M = N / R;
+    for (int b = threadIdx.x; b < 480 / R; b += ST) {
+        const int p = b / S, q = b - p * S;
+        float2 a[R], c[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            a[k] = x0[q + S * (p + k * M)];
+            c[k] = x1[q + S * (p + k * M)];
+        }
+        butterfly<R>(a);
+        butterfly<R>(c);
+        y0[q + S * (R * p)] = a[0];
+        y1[q + S * (R * p)] = c[0];
+#pragma unroll
+        for (int j = 1; j < R; j++) {
+            if (N == R) {
+                y0[q + S * (R * p + j)] = a[j];
+                y1[q + S * (R * p + j)] = c[j];
+            } else {
+                const float2 w = __ldg(&tw[j * p * S]);
+                y0[q + S * (R * p + j)] = cmul(a[j], w);
+                y1[q + S * (R * p + j)] = cmul(c[j], w);
+            }
+        }
+    }
+    __syncthreads();
+}
+// forward FFTs of a0[480] and a1[480]; results land in b0 and b1.
+__device__ void fft480x2(float2* a0, float2* b0, float2* a1, float2* b1, const float2* tw) {
+    stockham_pass2<4, 480, 1>(a0, b0, a1, b1, tw);
+    stockham_pass2<4, 120, 4>(b0, a0, b1, a1, tw);
+    stockham_pass2<5, 30, 16>(a0, b0, a1, b1, tw);
+    stockham_pass2<3, 6, 80>(b0, a0, b1, a1, tw);
+    stockham_pass2<2, 2, 240>(a0, b0, a1, b1, tw);
+}
+
 // Band-weighted sums (src/lib.rs:65-82), balanced two-stage reduction driven by DeviceTables::bt_*.
 // NS = 3: ex = |X|^2, ep = |P|^2, exp = Re(X conj P) in one sweep (x, p: spectra in shared memory);
 // NS = 1: only |X|^2.  part: shared scratch [NS][BT_LANES].  All threads must call; contains two barriers.
@@ -132,48 +172,66 @@ __device__ __forceinline__ float interp_gain(const float* g, const DeviceTables*
     return (1.0f - f) * g[b] + f * g[b + 1];
 }
 
-// Windowed real FFT of hist[(start + i)], i < 960 (ring-indexed); writes X[0..480] (scaled by wnorm)
-// into xs (shared, 481 entries).  a/b: scratch FFT buffers.  src/features.rs:281-298.
-__device__ void windowed_rfft(const float* __restrict__ h, int start, const DeviceTables* __restrict__ tab, float2* a,
-                              float2* b, float2* xs) {
-    if ((start & 3) == 0) {
-        // 16-byte aligned window start (always true for lag 0): 128-bit loads; a float4 never straddles the ring wrap
+// Window * history -> FFT input (src/features.rs:281-290).  The 960 samples starting at ring position `start` are
+// fetched into registers first (issue_loads) and multiplied/stored later (store), so that the DRAM latency of the
+// second (pitch-lagged) window hides behind other work.
+struct WindowLoad {
+    float4 hv[2], wv[2];   // aligned path: samples 4q..4q+3 of q = tid, tid + 128
+    float2 hs[4], ws[4];   // unaligned path: complex element n = tid + 128 it
+    bool aligned;
+    __device__ __forceinline__ void issue_loads(const float* __restrict__ h, int start, const DeviceTables* __restrict__ tab) {
+        aligned = (start & 3) == 0;
+        if (aligned) {
 #pragma unroll
-        for (int it = 0; it < 2; it++) {
-            const int q = threadIdx.x + it * ST;
-            if (q < WINDOW_SIZE / 4) {
-                int pos = start + 4 * q;
-                if (pos >= HIST_CAP) pos -= HIST_CAP;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(h + pos));
-                const float4 w = __ldg(reinterpret_cast<const float4*>(tab->window) + q);
-                reinterpret_cast<float4*>(a)[q] = make_float4(v.x * w.x, v.y * w.y, v.z * w.z, v.w * w.w);
+            for (int it = 0; it < 2; it++) {
+                const int q = threadIdx.x + it * ST;
+                hv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                wv[it] = hv[it];
+                if (q < WINDOW_SIZE / 4) {
+                    int pos = start + 4 * q;  // a float4 never straddles the ring wrap (start and HIST_CAP are multiples of 4)
+                    if (pos >= HIST_CAP) pos -= HIST_CAP;
+                    hv[it] = __ldg(reinterpret_cast<const float4*>(h + pos));
+                    wv[it] = __ldg(reinterpret_cast<const float4*>(tab->window) + q);
+                }
             }
-        }
-    } else {
-        float2 hv[4], wv[4];
+        } else {
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int n = threadIdx.x + it * ST;
-            hv[it] = make_float2(0.f, 0.f);
-            wv[it] = hv[it];
-            if (n < 480) {
-                int p0 = start + 2 * n;
-                if (p0 >= HIST_CAP) p0 -= HIST_CAP;
-                int p1 = p0 + 1;
-                if (p1 >= HIST_CAP) p1 -= HIST_CAP;
-                hv[it] = make_float2(__ldg(h + p0), __ldg(h + p1));
-                wv[it] = __ldg(reinterpret_cast<const float2*>(tab->window) + n);
+            for (int it = 0; it < 4; it++) {
+                const int n = threadIdx.x + it * ST;
+                hs[it] = make_float2(0.f, 0.f);
+                ws[it] = hs[it];
+                if (n < 480) {
+                    int p0 = start + 2 * n;
+                    if (p0 >= HIST_CAP) p0 -= HIST_CAP;
+                    int p1 = p0 + 1;
+                    if (p1 >= HIST_CAP) p1 -= HIST_CAP;
+                    hs[it] = make_float2(__ldg(h + p0), __ldg(h + p1));
+                    ws[it] = __ldg(reinterpret_cast<const float2*>(tab->window) + n);
+                }
             }
-        }
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int n = threadIdx.x + it * ST;
-            if (n < 480) a[n] = make_float2(hv[it].x * wv[it].x, hv[it].y * wv[it].y);
         }
     }
-    __syncthreads();
-    fft480(a, b, tab->tw480);
-    // even/odd split, bins k and 480-k together (tw960[480-k] = -conj(tw960[k]))
+    __device__ __forceinline__ void store(float2* a) const {
+        if (aligned) {
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int q = threadIdx.x + it * ST;
+                if (q < WINDOW_SIZE / 4)
+                    reinterpret_cast<float4*>(a)[q] = make_float4(hv[it].x * wv[it].x, hv[it].y * wv[it].y, hv[it].z * wv[it].z, hv[it].w * wv[it].w);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                const int n = threadIdx.x + it * ST;
+                if (n < 480) a[n] = make_float2(hs[it].x * ws[it].x, hs[it].y * ws[it].y);
+            }
+        }
+    }
+};
+
+// even/odd split of a 480-point complex FFT b into the 481 bins of the 960-point real FFT, scaled by wnorm
+// (src/features.rs:290-295); bins k and 480-k together (tw960[480-k] = -conj(tw960[k])).  No barrier inside.
+__device__ __forceinline__ void rfft_post(const float2* b, float2* xs, const DeviceTables* __restrict__ tab) {
     const float wn = tab->wnorm;
 #pragma unroll
     for (int it = 0; it < 2; it++) {
@@ -195,17 +253,16 @@ __device__ void windowed_rfft(const float* __restrict__ h, int start, const Devi
             if (k != 240) xs[480 - k] = r1;
         }
     }
-    __syncthreads();
 }
 
 // ================================================================================================
 // K3: analysis -- X, P, band energies, features (src/features.rs:115-219)
 // ================================================================================================
 __global__ void __launch_bounds__(ST) analysis_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab, int hbase) {
-    __shared__ __align__(16) float2 fa_[480];
-    __shared__ __align__(16) float2 fb_[480];
-    __shared__ __align__(16) float2 xs[FREQ_SIZE + 1];
-    __shared__ __align__(16) float2 ps[FREQ_SIZE + 1];
+    __shared__ __align__(16) float2 xa[FREQ_SIZE + 1];  // X: FFT ping buffer, then the 481-bin spectrum
+    __shared__ __align__(16) float2 xb[480];            // X: FFT pong buffer
+    __shared__ __align__(16) float2 pa[FREQ_SIZE + 1];  // P: the same for the pitch-lagged window
+    __shared__ __align__(16) float2 pb[480];
     __shared__ float part[3 * BT_LANES];
     __shared__ float s_ex[NB_BANDS], s_ep[NB_BANDS], s_exp[NB_BANDS], s_tmp[NB_BANDS], s_ly[NB_BANDS];
     __shared__ float s_feat[NB_FEATURES];
@@ -217,14 +274,24 @@ __global__ void __launch_bounds__(ST) analysis_kernel(BatchBuffers bb, const Dev
     const float* h = bb.hist + (size_t)s * HIST_CAP;
     const int pitch = bb.pitch[s];
 
-    // ---- X = rfft(window * input_mem[768..1728]) ----
+    // X = rfft(window * input_mem[768..1728]),  P = rfft(window * input_mem[768-pitch .. 1728-pitch]): all global
+    // loads are issued before the first use, then both transforms advance together.
     int start = hbase + (PITCH_BUF_SIZE - WINDOW_SIZE);
     if (start >= HIST_CAP) start -= HIST_CAP;
-    windowed_rfft(h, start, tab, fa_, fb_, xs);
-    // ---- P = rfft(window * input_mem[768-pitch .. 1728-pitch]) ----
+    WindowLoad wx, wp;
+    wx.issue_loads(h, start, tab);
     start = hbase + (PITCH_BUF_SIZE - WINDOW_SIZE) - pitch;  // >= 0 since pitch <= 768
     if (start >= HIST_CAP) start -= HIST_CAP;
-    windowed_rfft(h, start, tab, fa_, fb_, ps);
+    wp.issue_loads(h, start, tab);
+    wx.store(xa);
+    wp.store(pa);
+    __syncthreads();
+    fft480x2(xa, xb, pa, pb, tab->tw480);
+    float2* xs = xa;
+    float2* ps = pa;
+    rfft_post(xb, xs, tab);
+    rfft_post(pb, ps, tab);
+    __syncthreads();
 
     float2* Xg = bb.X + (size_t)s * FREQ_SIZE;
     float2* Pg = bb.P + (size_t)s * NB_BINS_BANDED;
@@ -345,31 +412,40 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
     __shared__ float s_g[NB_BANDS], s_r[NB_BANDS], s_ne[NB_BANDS], s_ex[NB_BANDS];
 
     const int s = blockIdx.x, tid = threadIdx.x;
-    const int silent = bb.silence[s];
+    // every global load of the block is issued up front (one DRAM round trip instead of a chain of dependent ones)
     const float2* Xg = bb.X + (size_t)s * FREQ_SIZE;
-    for (int k = tid; k <= 480; k += ST) xs[k] = Xg[k];
+    const float2* Pg = bb.P + (size_t)s * NB_BINS_BANDED;
+    float2 xv[4], pv[4];
+    int bidx[4];
+    float bfr[4];
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int k = tid + it * ST;
+        xv[it] = k <= 480 ? __ldg(Xg + k) : make_float2(0.f, 0.f);
+        pv[it] = k < NB_BINS_BANDED ? __ldg(Pg + k) : make_float2(0.f, 0.f);
+        bidx[it] = k < NB_BINS_BANDED ? __ldg(&tab->band_of[k]) : 0;
+        bfr[it] = k < NB_BINS_BANDED ? __ldg(&tab->band_frac[k]) : 0.0f;
+    }
+    float b_e = 0.f, b_g = 0.f, b_ex = 0.f, b_ep = 0.f, b_lg = 0.f;
+    if (tid < NB_BANDS) {
+        b_e = bb.exp[(size_t)s * NB_BANDS + tid];
+        b_g = bb.gains[(size_t)s * NB_BANDS + tid];
+        b_ex = bb.ex[(size_t)s * NB_BANDS + tid];
+        b_ep = bb.ep[(size_t)s * NB_BANDS + tid];
+        b_lg = bb.lastg[(size_t)s * NB_BANDS + tid];
+    }
+    const float vad_in = bb.vad[s];
+    const int silent = bb.silence[s];
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int k = tid + it * ST;
+        if (k <= 480) xs[k] = xv[it];
+    }
 
     if (!silent) {
-        const float2* Pg = bb.P + (size_t)s * NB_BINS_BANDED;
-        // per-thread interpolation coordinates of bins tid, tid+128, tid+256, tid+384
-        int bidx[4];
-        float bfr[4];
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int k = tid + it * ST;
-            bidx[it] = k < NB_BINS_BANDED ? tab->band_of[k] : 0;
-            bfr[it] = k < NB_BINS_BANDED ? tab->band_frac[k] : 0.0f;
-        }
-        float2 pv[4];
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int k = tid + it * ST;
-            pv[it] = k < NB_BINS_BANDED ? Pg[k] : make_float2(0.f, 0.f);
-        }
         if (tid < NB_BANDS) {
             // r (src/features.rs:226-235)
-            float e = bb.exp[(size_t)s * NB_BANDS + tid], g = bb.gains[(size_t)s * NB_BANDS + tid];
-            float ex = bb.ex[(size_t)s * NB_BANDS + tid], ep = bb.ep[(size_t)s * NB_BANDS + tid];
+            const float e = b_e, g = b_g, ex = b_ex, ep = b_ep;
             float r;
             if (e > g) {
                 r = 1.0f;
@@ -384,8 +460,7 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
             s_r[tid] = r;
             s_ex[tid] = ex;
             // gain floor (src/denoise.rs:106-109)
-            float lg = bb.lastg[(size_t)s * NB_BANDS + tid];
-            float gg = fmaxf(g, 0.6f * lg);
+            float gg = fmaxf(g, 0.6f * b_lg);
             s_g[tid] = gg;
             bb.lastg[(size_t)s * NB_BANDS + tid] = gg;
         }
@@ -476,7 +551,7 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
     }
     __syncthreads();
     for (int q = tid; q < FRAME_SIZE / 4; q += ST) reinterpret_cast<float4*>(sm)[q] = reinterpret_cast<const float4*>(fa_)[q];
-    if (tid == 0 && vad_out) vad_out[s] = silent ? 0.0f : bb.vad[s];
+    if (tid == 0 && vad_out) vad_out[s] = silent ? 0.0f : vad_in;
 }
 
 cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, float* out, long stream_stride, float* vad_out,

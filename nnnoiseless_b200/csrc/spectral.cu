@@ -258,7 +258,7 @@ __device__ __forceinline__ void rfft_post(const float2* b, float2* xs, const Dev
 // ================================================================================================
 // K3: analysis -- X, P, band energies, features (src/features.rs:115-219)
 // ================================================================================================
-__global__ void __launch_bounds__(ST) analysis_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab, int hbase) {
+__global__ void __launch_bounds__(ST, 10) analysis_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab, int hbase) {
     __shared__ __align__(16) float2 xa[FREQ_SIZE + 1];  // X: FFT ping buffer, then the 481-bin spectrum
     __shared__ __align__(16) float2 xb[480];            // X: FFT pong buffer
     __shared__ __align__(16) float2 pa[FREQ_SIZE + 1];  // P: the same for the pitch-lagged window

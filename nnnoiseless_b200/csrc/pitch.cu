@@ -468,16 +468,28 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
     __syncthreads();
     PPROF(5);
 
-    // ---- Ph6b: the ten fine-search lags of every stream (src/pitch.rs:88-96): lane-task = (stream, window, lag); window
-    // starts are clamped into the valid range, which of the lags count as candidates is decided in Ph8.  A single warp
-    // sustains only ~0.5 instructions/cycle, so the 160 short tasks are spread over all warps instead of being folded
-    // into two long sliding-window tasks. ----
-    for (int L = tid; L < SB * 10; L += NT) {
-        const int s = L / 10, c = L - s * 10, wdw = c >= 5;
-        const int ctr = 2 * SI[wdw * SB + s];
-        const int i = min(max(ctr - 2, 0), NL2 - 5) + (c - 5 * wdw);
-        const float* prow = P + s * P_LD;
-        FX[s * FX_LD + c] = fmaxf(inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + i), -1.0f);
+    // ---- Ph6b: the two 5-lag fine windows of every stream (src/pitch.rs:88-96), each split into a 3-lag and a
+    // 2-lag sliding window so that two warps share the work.  lane-task = (stream, window): lags i0c .. i0c+4, i0c =
+    // window start clamped into the valid range; which of them count as candidates is decided in Ph8. ----
+    if (warp == 2 || warp == 3) {
+        for (int L = lane; L < 2 * SB; L += 32) {
+            const int s = L >> 1, wdw = L & 1;
+            const int ctr = 2 * SI[wdw * SB + s];
+            const int i0c = min(max(ctr - 2, 0), NL2 - 5);
+            const float* prow = P + s * P_LD;
+            const float4* xr = reinterpret_cast<const float4*>(prow + HALF_MAX);
+            if (warp == 2) {
+                float out[3];
+                inner_prod_window<3>(xr, prow + i0c, out);
+#pragma unroll
+                for (int c = 0; c < 3; c++) FX[s * FX_LD + wdw * 5 + c] = fmaxf(out[c], -1.0f);
+            } else {
+                float out[2];
+                inner_prod_window<2>(xr, prow + i0c + 3, out);
+#pragma unroll
+                for (int c = 0; c < 2; c++) FX[s * FX_LD + wdw * 5 + 3 + c] = fmaxf(out[c], -1.0f);
+            }
+        }
     }
     __syncthreads();
     PPROF(6);
@@ -631,33 +643,22 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         float pg = (best_yy <= best_xy) ? 1.0f : __fdiv_rn(best_xy, fa(best_yy, 1.0f));
         pg = fminf(pg, g);
 
-        SI[3 * SB + ls] = t;
-        XX[ls] = pg;  // xx is no longer needed: the slot carries the pitch gain to the last phase
-    }
-    __syncthreads();
-    PPROF(9);
-
-    // +-1 refinement (src/pitch.rs:205-218): xcorr at lags t-1, t, t+1; lane-task = (stream, lag)
-    for (int L = tid; L < SB * 3; L += NT) {
-        const int s = L / 3, c = L - s * 3;
-        const int t = SI[3 * SB + s];
-        const float* prow = P + s * P_LD;
-        IPR[s * IPR_LD + c] = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (t + c - 1));
-    }
-    __syncthreads();
-    if (warp == 0 && lane < ns) {
-        const float* ipr = IPR + lane * IPR_LD;
-        const float x_0 = ipr[0], x_1 = ipr[1], x_2 = ipr[2];
-        const int t = SI[3 * SB + lane];
+        // xcorr at lags t-1, t, t+1: one sliding window starting at lag t+1 (lowest address)
+        float xc3[3];
+        const float* prow = P + ls * P_LD;
+        inner_prod_window<3>(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (t + 1), xc3);
+        const float x_0 = xc3[2], x_1 = xc3[1], x_2 = xc3[0];  // window slot c <-> lag t + 1 - c
         int offset = 0;
         if (fs(x_2, x_0) > fm(0.7f, fs(x_1, x_0))) offset = 1;
         else if (fs(x_0, x_2) > fm(0.7f, fs(x_1, x_2))) offset = -1;
         const int tf = max(2 * t + offset, PITCH_MIN_PERIOD);
-        pitch_out[s0 + lane] = tf;
-        last_period[s0 + lane] = tf;
-        last_gain[s0 + lane] = XX[lane];
+        if (lane < ns) {
+            pitch_out[s0 + lane] = tf;
+            last_period[s0 + lane] = tf;
+            last_gain[s0 + lane] = pg;
+        }
     }
-    PPROF(10);
+    PPROF(9);
 }
 
 }  // namespace

@@ -16,7 +16,7 @@ L.nnb_pitch_prof_read(buf, 1)
 b.process_host(xt[2:])
 L.nnb_pitch_prof_read(buf, 0)
 nblk = (B + 15) // 16 * 4
-names = ["downsample", "autocorr", "lpc", "fir", "xcorr+chains", "select+yn2", "fine lags", "fine select", "rd inner", "ladder", "refinement", "-"]
+names = ["downsample", "autocorr", "lpc", "fir", "xcorr+chains", "select+yn2", "fine windows", "fine select", "rd inner", "ladder+final", "-", "-"]
 tot = sum(buf)
 for i in range(11):
     if buf[i]:

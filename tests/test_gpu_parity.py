@@ -239,3 +239,65 @@ def test_baseline_size_batch_properties(builtin_bytes):
     assert bool((tiles == tiles[:, :1]).all())
     assert bool((vad.view(T, B // D, D) == vad.view(T, B // D, D)[:, :1]).all())
     check_against_oracle(tiles[:, 0].cpu().numpy(), vad[:, :D].cpu().numpy(), b.taps()["pitch"][:D], ref, x)
+
+
+def test_frame_pipeline_call_patterns_bitwise(builtin_bytes):
+    """The five-stream frame pipeline must be invisible: any split of the same frames into calls (host or device API,
+    T = 1 or many), and the serialised reference order (NNB_SERIAL=1), give bit-identical results."""
+    import os
+    import torch
+    B, T = 96, 23
+    x = np.ascontiguousarray(synth_streams(B, T, seed=77).reshape(B, T, 480).transpose(1, 0, 2))  # [T][B][480]
+    a = nb.DenoiseBatch(B)
+    o_ref, v_ref = a.process_host(x)
+    # irregular call sizes through the host API
+    b = nb.DenoiseBatch(B)
+    outs, vads, t = [], [], 0
+    for n in (1, 5, 2, 9, 1, 5):
+        o, v = b.process_host(x[t:t + n]); outs.append(o); vads.append(v); t += n
+    assert np.array_equal(np.concatenate(outs), o_ref) and np.array_equal(np.concatenate(vads), v_ref)
+    # device API on a torch stream, mixed with host-API calls on the same handle
+    c = nb.DenoiseBatch(B)
+    xd = torch.from_numpy(x).cuda()
+    od = torch.empty_like(xd)
+    vd = torch.empty(T, B, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        c.process_device(od[:10].data_ptr(), xd[:10].data_ptr(), vd[:10].data_ptr(), 10, 480, B * 480, st.cuda_stream)
+    st.synchronize()
+    o_mid, v_mid = c.process_host(x[10:14])
+    with torch.cuda.stream(st):
+        c.process_device(od[14:].data_ptr(), xd[14:].data_ptr(), vd[14:].data_ptr(), T - 14, 480, B * 480, st.cuda_stream)
+    st.synchronize()
+    got = np.concatenate([od[:10].cpu().numpy(), o_mid, od[14:].cpu().numpy()])
+    assert np.array_equal(got, o_ref)
+    assert np.array_equal(np.concatenate([vd[:10].cpu().numpy(), v_mid, vd[14:].cpu().numpy()]), v_ref)
+    # two handles interleaved frame by frame do not disturb each other
+    d1, d2 = nb.DenoiseBatch(B), nb.DenoiseBatch(B)
+    for t in range(6):
+        o1, _ = d1.process_host(x[t:t + 1])
+        o2, _ = d2.process_host(x[t:t + 1])
+        assert np.array_equal(o1[0], o_ref[t]) and np.array_equal(o2[0], o_ref[t])
+    # serialised single-stream execution = the same bits
+    os.environ["NNB_SERIAL"] = "1"
+    try:
+        e = nb.DenoiseBatch(B)
+    finally:
+        del os.environ["NNB_SERIAL"]
+    o_ser, v_ser = e.process_host(x)
+    assert np.array_equal(o_ser, o_ref) and np.array_equal(v_ser, v_ref)
+
+
+def test_fp32_gru_kernel_agrees_with_tensor_core_kernel(builtin_bytes):
+    """NNB_RNN_FP32=1 selects the CUDA-core GRU kernel: both stay within the oracle tolerance of each other."""
+    import os
+    B, T = 40, 12
+    x = np.ascontiguousarray(synth_streams(B, T, seed=78).reshape(B, T, 480).transpose(1, 0, 2))
+    o_tc, v_tc = nb.DenoiseBatch(B).process_host(x)
+    os.environ["NNB_RNN_FP32"] = "1"
+    try:
+        f = nb.DenoiseBatch(B)
+    finally:
+        del os.environ["NNB_RNN_FP32"]
+    o_fp, v_fp = f.process_host(x)
+    assert rel_rms(o_tc, o_fp) <= OUT_REL_RMS and np.abs(v_tc - v_fp).max() <= VAD_ATOL

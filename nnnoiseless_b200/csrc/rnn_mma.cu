@@ -20,9 +20,12 @@ namespace nnb {
 namespace {
 
 constexpr int TS = 32;      // streams per block = two m16 row tiles
-constexpr int NWARP = 4;
+#ifndef RNN_NWARP
+#define RNN_NWARP 8
+#endif
+constexpr int NWARP = RNN_NWARP;
 constexpr int NT = NWARP * 32;
-constexpr int MAXOT = 4;    // output tiles (8 neurons) per warp: covers layers up to 128 neurons
+constexpr int MAXOT = 16 / NWARP;  // output tiles (8 neurons) per warp: NWARP * MAXOT tiles cover layers up to 128 neurons
 constexpr float WEIGHTS_SCALE = 1.0f / 256.0f;
 
 __device__ __forceinline__ float tansig_approx(float x, const float* __restrict__ table) {
@@ -226,7 +229,10 @@ __device__ void gru_layer(const MmaPhase& pzr, const MmaPhase& ph, int act, int 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT) rnn_mma_kernel(BatchBuffers bb, DeviceModelMma m, const DeviceTables* __restrict__ tab) {
+#ifndef RNN_MINB
+#define RNN_MINB 1
+#endif
+__global__ void __launch_bounds__(NT, RNN_MINB) rnn_mma_kernel(BatchBuffers bb, DeviceModelMma m, const DeviceTables* __restrict__ tab) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int kp = m.kp, hs = m.hs;
     __half* Ahi = reinterpret_cast<__half*>(smraw);

@@ -305,6 +305,27 @@ def run_b200(args):
     e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": Te * B * FRAME * 4,
            "d2h_bytes_per_step": Te * B * (FRAME * 4 + 4), "frames_per_call": Te,
            "api": "rnnoise_batch_process_host (pinned host buffers, H2D + 5 kernels/frame + D2H, synchronous)"}
+    # same through the 16-bit PCM entry point (int16 in/out, conversion fused into the kernels): half the PCIe bytes
+    hx16 = torch.empty(Te, B, FRAME, dtype=torch.int16).pin_memory()
+    hx16.copy_(x[:Te].to(torch.int16).cpu())
+    ho16 = torch.empty(Te, B, FRAME, dtype=torch.int16).pin_memory()
+
+    def e2e16_step():
+        rc = L.rnnoise_batch_process_pcm16_host(batch._h, C.c_void_p(ho16.data_ptr()), C.c_void_p(hx16.data_ptr()),
+                                                C.c_void_p(hv.data_ptr()), Te)
+        assert rc == 0, nb.last_error()
+
+    e2e16_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        e2e16_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e["pcm16"] = {"value": world * B * Te * ne / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": Te * B * FRAME * 2,
+                    "d2h_bytes_per_step": Te * B * (FRAME * 2 + 4), "api": "rnnoise_batch_process_pcm16_host"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample of the same workload ----
     cpu = None

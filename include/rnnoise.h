@@ -94,6 +94,12 @@ int rnnoise_batch_reset(RNNoiseBatch *b);
 int rnnoise_batch_process_device(RNNoiseBatch *b, float *out, const float *in, float *vad, int n_frames,
                                  long stream_stride, long frame_stride, void *cuda_stream);
 
+/* The same with 16-bit PCM device buffers (strides in samples): the int16 -> float widening and the
+ * clamp + round-to-nearest back to int16 (src/nnnoiseless.rs:147-177, test_data/rnnoise_demo.c:51-55) happen
+ * inside the first and last kernel of the path. */
+int rnnoise_batch_process_device_pcm16(RNNoiseBatch *b, short *out, const short *in, float *vad, int n_frames,
+                                       long stream_stride, long frame_stride, void *cuda_stream);
+
 /* Same through HOST buffers: copies in -> device, runs, copies out/vad back, synchronises.
  * Layout [n_frames][n_streams][480] (frame-major), vad [n_frames][n_streams]. */
 int rnnoise_batch_process_host(RNNoiseBatch *b, float *out, const float *in, float *vad, int n_frames);

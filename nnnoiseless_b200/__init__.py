@@ -29,7 +29,8 @@ C_ABI_SYMBOLS = [
     "rnnoise_process_frame", "rnnoise_model_from_file", "rnnoise_model_free",
     "rnnoise_model_from_bytes", "rnnoise_model_from_text", "rnnoise_model_bytes",
     "rnnoise_batch_create", "rnnoise_batch_destroy", "rnnoise_batch_streams", "rnnoise_batch_reset",
-    "rnnoise_batch_process_device", "rnnoise_batch_process_host", "rnnoise_batch_process_pcm16_host",
+    "rnnoise_batch_process_device", "rnnoise_batch_process_device_pcm16", "rnnoise_batch_process_host",
+    "rnnoise_batch_process_pcm16_host",
     "rnnoise_batch_get_taps", "rnnoise_batch_profile_step", "rnnoise_kernel_name",
     "rnnoise_kernel_launches", "rnnoise_last_error",
 ]
@@ -78,6 +79,8 @@ def lib():
     L.rnnoise_batch_reset.argtypes = [vp]
     L.rnnoise_batch_process_device.restype = ci
     L.rnnoise_batch_process_device.argtypes = [vp, vp, vp, vp, ci, C.c_long, C.c_long, vp]
+    L.rnnoise_batch_process_device_pcm16.restype = ci
+    L.rnnoise_batch_process_device_pcm16.argtypes = [vp, vp, vp, vp, ci, C.c_long, C.c_long, vp]
     L.rnnoise_batch_process_host.restype = ci
     L.rnnoise_batch_process_host.argtypes = [vp, vp, vp, vp, ci]
     L.rnnoise_batch_process_pcm16_host.restype = ci
@@ -217,9 +220,10 @@ class DenoiseBatch:
         return out, vad
 
     def process_device(self, out_ptr: int, in_ptr: int, vad_ptr: int, n_frames: int, stream_stride: int,
-                       frame_stride: int, cuda_stream: int = 0):
-        """Raw device pointers (e.g. torch tensors' data_ptr()); strides in floats."""
-        rc = lib().rnnoise_batch_process_device(self._h, C.c_void_p(out_ptr), C.c_void_p(in_ptr),
+                       frame_stride: int, cuda_stream: int = 0, pcm16: bool = False):
+        """Raw device pointers (e.g. torch tensors' data_ptr()); strides in samples (float32, or int16 if pcm16)."""
+        fn = lib().rnnoise_batch_process_device_pcm16 if pcm16 else lib().rnnoise_batch_process_device
+        rc = fn(self._h, C.c_void_p(out_ptr), C.c_void_p(in_ptr),
                                                 C.c_void_p(vad_ptr) if vad_ptr else None, int(n_frames),
                                                 int(stream_stride), int(frame_stride),
                                                 C.c_void_p(cuda_stream) if cuda_stream else None)

@@ -28,7 +28,9 @@ constexpr int HP_CHUNK = 80;
 constexpr int HP_LD = HP_CHUNK + 1;
 static_assert(FRAME_SIZE % HP_CHUNK == 0 && HP_CHUNK % 4 == 0, "chunking must tile the frame");
 
-__global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const float* __restrict__ in, long stream_stride,
+// TIn = float (the reference's f32-in-i16-range samples) or short (16-bit PCM, src/nnnoiseless.rs:147-177 front-end fused in)
+template <typename TIn>
+__global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const TIn* __restrict__ in, long stream_stride,
                                                                float* __restrict__ hist, float* __restrict__ hp_mem,
                                                                int n_streams, int slot, int vec_ok) {
     __shared__ float tile[HP_STREAMS * HP_LD];
@@ -43,17 +45,30 @@ __global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const float* __re
     }
     constexpr int Q = HP_CHUNK / 4;  // float4 per row per chunk
     for (int c = 0; c < FRAME_SIZE / HP_CHUNK; c++) {
-        if (vec_ok) {
+        if (vec_ok && sizeof(TIn) == 4) {
             for (int idx = tid; idx < ns * Q; idx += HP_THREADS) {
                 const int row = idx / Q, q = idx - row * Q;
                 const float4 v = __ldg(reinterpret_cast<const float4*>(in + (long)(s0 + row) * stream_stride + c * HP_CHUNK) + q);
                 float* t = tile + row * HP_LD + 4 * q;
                 t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
             }
+        } else if (vec_ok) {  // 16-bit PCM: 8 samples per 128-bit load
+            constexpr int Q8 = HP_CHUNK / 8;
+            for (int idx = tid; idx < ns * Q8; idx += HP_THREADS) {
+                const int row = idx / Q8, q = idx - row * Q8;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (long)(s0 + row) * stream_stride + c * HP_CHUNK) + q);
+                float* t = tile + row * HP_LD + 8 * q;
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    t[2 * k] = (float)(short)(w[k] & 0xffffu);
+                    t[2 * k + 1] = (float)(short)(w[k] >> 16);
+                }
+            }
         } else {
             for (int idx = tid; idx < ns * HP_CHUNK; idx += HP_THREADS) {
                 const int row = idx / HP_CHUNK, i = idx - row * HP_CHUNK;
-                tile[row * HP_LD + i] = in[(long)(s0 + row) * stream_stride + c * HP_CHUNK + i];
+                tile[row * HP_LD + i] = (float)in[(long)(s0 + row) * stream_stride + c * HP_CHUNK + i];
             }
         }
         __syncthreads();
@@ -86,10 +101,14 @@ __global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const float* __re
     }
 }
 
-cudaError_t launch_hp_filter(const BatchBuffers& b, const float* in, long stream_stride, int slot, cudaStream_t st) {
-    int vec_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (stream_stride % 4 == 0);
+cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, long stream_stride, int slot, cudaStream_t st) {
+    const int per16 = pcm16 ? 8 : 4;  // elements per 128-bit load
+    int vec_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (stream_stride % per16 == 0);
     int grid = (b.n_streams + HP_STREAMS - 1) / HP_STREAMS;
-    hp_filter_kernel<<<grid, HP_THREADS, 0, st>>>(in, stream_stride, b.hist, b.hp_mem, b.n_streams, slot, vec_ok);
+    if (pcm16)
+        hp_filter_kernel<short><<<grid, HP_THREADS, 0, st>>>(static_cast<const short*>(in), stream_stride, b.hist, b.hp_mem, b.n_streams, slot, vec_ok);
+    else
+        hp_filter_kernel<float><<<grid, HP_THREADS, 0, st>>>(static_cast<const float*>(in), stream_stride, b.hist, b.hp_mem, b.n_streams, slot, vec_ok);
     return cudaGetLastError();
 }
 

@@ -322,19 +322,6 @@ int upload_model_mma(const HostModel& m, UploadedMma* um, cudaStream_t st) {
     return 0;
 }
 
-// ---- pcm16 front-end kernels (src/nnnoiseless.rs:147-177, test_data/rnnoise_demo.c:51-55) ---------------
-__global__ void pcm16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (float)in[i];
-}
-__global__ void f32_to_pcm16_kernel(const float* __restrict__ in, short* __restrict__ out, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        float v = fminf(fmaxf(in[i], -32768.0f), 32767.0f);  // clamp, then round half away from zero
-        out[i] = (short)roundf(v);
-    }
-}
-
 }  // namespace
 
 // ---- the batch handle -----------------------------------------------------------------------------------
@@ -537,28 +524,29 @@ int ensure_stage(RNNoiseBatch* b, int n_frames, bool pcm) {
     return 0;
 }
 
-int launch_stage(RNNoiseBatch* b, int i, const BatchBuffers& v, float* out, const float* in, float* vad, long stream_stride, int slot,
+// in/out are float samples, or 16-bit PCM when pcm is set (element strides either way)
+int launch_stage(RNNoiseBatch* b, int i, const BatchBuffers& v, void* out, const void* in, bool pcm, float* vad, long stream_stride, int slot,
                  cudaStream_t s) {
     switch (i) {
-        case 0: CK(launch_hp_filter(v, in, stream_stride, slot, s)); break;
+        case 0: CK(launch_hp_filter(v, in, pcm, stream_stride, slot, s)); break;
         case 1: CK(launch_pitch(v, slot, s)); break;
         case 2: CK(launch_analysis(v, b->d_tab, slot, s)); break;
         case 3:
             if (b->rnn_fp32) CK(launch_rnn(v, b->um.dm, b->d_tab, s));
             else CK(launch_rnn_mma(v, b->umm.dm, b->d_tab, s));
             break;
-        default: CK(launch_synthesis(v, b->d_tab, out, stream_stride, vad, s)); break;
+        default: CK(launch_synthesis(v, b->d_tab, out, pcm, stream_stride, vad, s)); break;
     }
     return 0;
 }
 
 // One frame for all streams, serialised on ONE stream (profiling, NNB_SERIAL=1).  tev (optional): kNumKernels + 1 timing events.
-int step_serial(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, cudaStream_t s, cudaEvent_t* tev = nullptr) {
+int step_serial(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad, long stream_stride, cudaStream_t s, cudaEvent_t* tev = nullptr) {
     const int slot = (int)(b->frame % HIST_SLOTS);
     const BatchBuffers v = view(b, b->frame);
     for (int i = 0; i < kNumKernels; i++) {
         if (tev) CK(cudaEventRecord(tev[i], s));
-        if (launch_stage(b, i, v, out, in, vad, stream_stride, slot, s)) return -1;
+        if (launch_stage(b, i, v, out, in, pcm, vad, stream_stride, slot, s)) return -1;
     }
     if (tev) CK(cudaEventRecord(tev[kNumKernels], s));
     g_launches.fetch_add(kNumKernels, std::memory_order_relaxed);
@@ -567,7 +555,7 @@ int step_serial(RNNoiseBatch* b, float* out, const float* in, float* vad, long s
 }
 
 // One frame for all streams on the five stage streams.  in_ready (optional): event the first stage must wait for.
-int step_pipelined(RNNoiseBatch* b, float* out, const float* in, float* vad, long stream_stride, cudaEvent_t in_ready) {
+int step_pipelined(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad, long stream_stride, cudaEvent_t in_ready) {
     const unsigned long long f = b->frame;
     const int slot = (int)(f % HIST_SLOTS), e = (int)(f % kEvRing);
     const BatchBuffers v = view(b, f);
@@ -575,7 +563,7 @@ int step_pipelined(RNNoiseBatch* b, float* out, const float* in, float* vad, lon
     if (f >= (unsigned long long)PIPE_DEPTH) CK(cudaStreamWaitEvent(b->st[0], b->ev[kNumKernels - 1][(int)((f - PIPE_DEPTH) % kEvRing)], 0));
     for (int i = 0; i < kNumKernels; i++) {
         if (i > 0) CK(cudaStreamWaitEvent(b->st[i], b->ev[i - 1][e], 0));
-        if (launch_stage(b, i, v, out, in, vad, stream_stride, slot, b->st[i])) return -1;
+        if (launch_stage(b, i, v, out, in, pcm, vad, stream_stride, slot, b->st[i])) return -1;
         CK(cudaEventRecord(b->ev[i][e], b->st[i]));
     }
     g_launches.fetch_add(kNumKernels, std::memory_order_relaxed);
@@ -670,19 +658,19 @@ int rnnoise_batch_reset(RNNoiseBatch* b) {
     return zero_state(b);
 }
 
-int rnnoise_batch_process_device(RNNoiseBatch* b, float* out, const float* in, float* vad, int n_frames, long stream_stride,
-                                 long frame_stride, void* cuda_stream) {
+static int process_device_impl(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad, int n_frames, long stream_stride,
+                               long frame_stride, void* cuda_stream) {
     if (!b || !out || !in) return fail("null argument");
     if (n_frames < 0) return fail("negative n_frames");
     if (n_frames == 0) return 0;
     CK(cudaSetDevice(b->device));
+    const size_t esz = pcm ? sizeof(short) : sizeof(float);
+    auto at = [&](const void* p, int t) { return (void*)((char*)p + (size_t)t * frame_stride * esz); };
     cudaStream_t us = (cudaStream_t)cuda_stream;
     if (b->serial) {
         cudaStream_t s = us ? us : b->st[0];
         for (int t = 0; t < n_frames; t++)
-            if (step_serial(b, out + (long)t * frame_stride, in + (long)t * frame_stride, vad ? vad + (size_t)t * b->n_streams : nullptr,
-                            stream_stride, s))
-                return -1;
+            if (step_serial(b, at(out, t), at(in, t), pcm, vad ? vad + (size_t)t * b->n_streams : nullptr, stream_stride, s)) return -1;
         if (!us) CK(cudaStreamSynchronize(s));
         return 0;
     }
@@ -692,8 +680,8 @@ int rnnoise_batch_process_device(RNNoiseBatch* b, float* out, const float* in, f
         ready = b->ev_call;
     }
     for (int t = 0; t < n_frames; t++) {
-        if (step_pipelined(b, out + (long)t * frame_stride, in + (long)t * frame_stride, vad ? vad + (size_t)t * b->n_streams : nullptr,
-                           stream_stride, t == 0 ? ready : nullptr))
+        if (step_pipelined(b, at(out, t), at(in, t), pcm, vad ? vad + (size_t)t * b->n_streams : nullptr, stream_stride,
+                           t == 0 ? ready : nullptr))
             return -1;
     }
     if (us) {
@@ -702,6 +690,16 @@ int rnnoise_batch_process_device(RNNoiseBatch* b, float* out, const float* in, f
         CK(cudaStreamSynchronize(b->st[kNumKernels - 1]));
     }
     return 0;
+}
+
+int rnnoise_batch_process_device(RNNoiseBatch* b, float* out, const float* in, float* vad, int n_frames, long stream_stride,
+                                 long frame_stride, void* cuda_stream) {
+    return process_device_impl(b, out, in, false, vad, n_frames, stream_stride, frame_stride, cuda_stream);
+}
+
+int rnnoise_batch_process_device_pcm16(RNNoiseBatch* b, short* out, const short* in, float* vad, int n_frames, long stream_stride,
+                                       long frame_stride, void* cuda_stream) {
+    return process_device_impl(b, out, in, true, vad, n_frames, stream_stride, frame_stride, cuda_stream);
 }
 
 const char* rnnoise_kernel_name(int i) { return (i >= 0 && i < kNumKernels) ? kKernelNames[i] : nullptr; }
@@ -715,7 +713,7 @@ int rnnoise_batch_profile_step(RNNoiseBatch* b, float* out, const float* in, flo
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->st[0];
     cudaEvent_t ev[kNumKernels + 1];
     for (int i = 0; i <= kNumKernels; i++) CK(cudaEventCreate(&ev[i]));
-    int rc = step_serial(b, out, in, vad, stream_stride, st, ev);
+    int rc = step_serial(b, out, in, false, vad, stream_stride, st, ev);
     if (rc == 0) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail("profile_step sync", e);
@@ -733,43 +731,31 @@ int rnnoise_batch_profile_step(RNNoiseBatch* b, float* out, const float* in, flo
 }
 
 // Host buffers: frame t is copied in on c_in, processed on the stage streams, copied out on c_out; copies of
-// neighbouring frames overlap the kernels (true overlap needs page-locked host memory).
-static int process_host_impl(RNNoiseBatch* b, float* out, const float* in, short* out16, const short* in16, float* vad, int n_frames) {
-    const bool pcm = in16 != nullptr;
+// neighbouring frames overlap the kernels (true overlap needs page-locked host memory).  16-bit PCM is consumed
+// and produced by the kernels directly (half the bytes over PCIe and HBM).
+static int process_host_impl(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad, int n_frames) {
     if (ensure_stage(b, n_frames, pcm)) return -1;
     const size_t B = (size_t)b->n_streams, fs = B * FRAME_SIZE;
-    const int th = 256;
-    const unsigned grid = (unsigned)((fs + th - 1) / th);
+    const size_t esz = pcm ? sizeof(short) : sizeof(float);
+    char* din = pcm ? (char*)b->stage_pcm_in : (char*)b->stage_in;
+    char* dout = pcm ? (char*)b->stage_pcm_out : (char*)b->stage_out;
     // everything issued earlier on the stage streams may still be reading/writing the staging buffers
     if (join_into(b, b->c_in)) return -1;
     for (int t = 0; t < n_frames; t++) {
         const int e = (int)(b->frame % kEvRing);
-        if (pcm) {
-            CK(cudaMemcpyAsync(b->stage_pcm_in + t * fs, in16 + t * fs, fs * sizeof(short), cudaMemcpyHostToDevice, b->c_in));
-            pcm16_to_f32_kernel<<<grid, th, 0, b->c_in>>>(b->stage_pcm_in + t * fs, b->stage_in + t * fs, fs);
-            CK(cudaGetLastError());
-        } else {
-            CK(cudaMemcpyAsync(b->stage_in + t * fs, in + t * fs, fs * sizeof(float), cudaMemcpyHostToDevice, b->c_in));
-        }
+        CK(cudaMemcpyAsync(din + t * fs * esz, (const char*)in + t * fs * esz, fs * esz, cudaMemcpyHostToDevice, b->c_in));
         CK(cudaEventRecord(b->ev_in[e], b->c_in));
         if (b->serial) {
             CK(cudaStreamWaitEvent(b->st[0], b->ev_in[e], 0));
-            if (step_serial(b, b->stage_out + t * fs, b->stage_in + t * fs, b->stage_vad + (size_t)t * B, FRAME_SIZE, b->st[0])) return -1;
+            if (step_serial(b, dout + t * fs * esz, din + t * fs * esz, pcm, b->stage_vad + (size_t)t * B, FRAME_SIZE, b->st[0])) return -1;
             CK(cudaEventRecord(b->ev[kNumKernels - 1][e], b->st[0]));
         } else {
-            if (step_pipelined(b, b->stage_out + t * fs, b->stage_in + t * fs, b->stage_vad + (size_t)t * B, FRAME_SIZE, b->ev_in[e])) return -1;
+            if (step_pipelined(b, dout + t * fs * esz, din + t * fs * esz, pcm, b->stage_vad + (size_t)t * B, FRAME_SIZE, b->ev_in[e])) return -1;
         }
         CK(cudaStreamWaitEvent(b->c_out, b->ev[kNumKernels - 1][e], 0));
-        if (pcm) {
-            f32_to_pcm16_kernel<<<grid, th, 0, b->c_out>>>(b->stage_out + t * fs, b->stage_pcm_out + t * fs, fs);
-            CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(out16 + t * fs, b->stage_pcm_out + t * fs, fs * sizeof(short), cudaMemcpyDeviceToHost, b->c_out));
-        } else {
-            CK(cudaMemcpyAsync(out + t * fs, b->stage_out + t * fs, fs * sizeof(float), cudaMemcpyDeviceToHost, b->c_out));
-        }
+        CK(cudaMemcpyAsync((char*)out + t * fs * esz, dout + t * fs * esz, fs * esz, cudaMemcpyDeviceToHost, b->c_out));
         if (vad) CK(cudaMemcpyAsync(vad + (size_t)t * B, b->stage_vad + (size_t)t * B, B * sizeof(float), cudaMemcpyDeviceToHost, b->c_out));
     }
-    if (pcm) g_launches.fetch_add(2ull * n_frames, std::memory_order_relaxed);
     CK(cudaStreamSynchronize(b->c_out));
     CK(cudaStreamSynchronize(b->c_in));
     return 0;
@@ -779,14 +765,14 @@ int rnnoise_batch_process_host(RNNoiseBatch* b, float* out, const float* in, flo
     if (!b || !out || !in) return fail("null argument");
     if (n_frames <= 0) return n_frames == 0 ? 0 : fail("negative n_frames");
     CK(cudaSetDevice(b->device));
-    return process_host_impl(b, out, in, nullptr, nullptr, vad, n_frames);
+    return process_host_impl(b, out, in, false, vad, n_frames);
 }
 
 int rnnoise_batch_process_pcm16_host(RNNoiseBatch* b, short* out, const short* in, float* vad, int n_frames) {
     if (!b || !out || !in) return fail("null argument");
     if (n_frames <= 0) return n_frames == 0 ? 0 : fail("negative n_frames");
     CK(cudaSetDevice(b->device));
-    return process_host_impl(b, nullptr, nullptr, out, in, vad, n_frames);
+    return process_host_impl(b, out, in, true, vad, n_frames);
 }
 
 int rnnoise_batch_get_taps(RNNoiseBatch* b, int* pitch, int* silence, float* features, float* gains) {

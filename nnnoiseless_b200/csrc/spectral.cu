@@ -402,8 +402,13 @@ cudaError_t launch_analysis(const BatchBuffers& b, const DeviceTables* tab, int 
 // K5: synthesis -- pitch filter, gain floor, band-gain interpolation, inverse FFT, overlap-add
 // (src/denoise.rs:102-115, src/features.rs:223-275)
 // ================================================================================================
+// TOut = float, or short: clamp to the int16 range then round half away from zero (what both reference front-ends do:
+// src/nnnoiseless.rs:152 `clamp().round() as i16`, test_data/rnnoise_demo.c:53 roundf).
+__device__ __forceinline__ short to_pcm16(float v) { return (short)roundf(fminf(fmaxf(v, -32768.0f), 32767.0f)); }
+
+template <typename TOut>
 __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab,
-                                                       float* __restrict__ out, long stream_stride,
+                                                       TOut* __restrict__ out, long stream_stride,
                                                        float* __restrict__ vad_out) {
     __shared__ __align__(16) float2 xs[FREQ_SIZE + 1];
     __shared__ __align__(16) float2 fa_[480];
@@ -525,10 +530,10 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
     __syncthreads();
     fft480(fa_, fb_, tab->tw480);
     float* sm = bb.synth_mem + (size_t)s * FRAME_SIZE;
-    float* o = out + (long)s * stream_stride;
+    TOut* o = out + (long)s * stream_stride;
     // time samples 4q..4q+3 = (re, -im) of fb_[2q], fb_[2q+1]; first half -> output (+ overlap memory),
-    // second half -> new overlap memory.  128-bit accesses when the caller's rows are 16-byte aligned.
-    const bool o_vec = ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+    // second half -> new overlap memory.  Vector stores when the caller's rows are aligned for them.
+    const bool o_vec = ((reinterpret_cast<uintptr_t>(o) & (4 * sizeof(TOut) - 1)) == 0);
 #pragma unroll
     for (int it = 0; it < 2; it++) {
         const int q = tid + it * ST;
@@ -539,10 +544,22 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
             if (q < FRAME_SIZE / 4) {
                 const float4 m = reinterpret_cast<const float4*>(sm)[q];
                 const float4 r = make_float4(v.x + m.x, v.y + m.y, v.z + m.z, v.w + m.w);
-                if (o_vec) {
-                    reinterpret_cast<float4*>(o)[q] = r;
+                if (sizeof(TOut) == 4) {
+                    float* of = reinterpret_cast<float*>(o);
+                    if (o_vec) {
+                        reinterpret_cast<float4*>(of)[q] = r;
+                    } else {
+                        of[4 * q] = r.x; of[4 * q + 1] = r.y; of[4 * q + 2] = r.z; of[4 * q + 3] = r.w;
+                    }
                 } else {
-                    o[4 * q] = r.x; o[4 * q + 1] = r.y; o[4 * q + 2] = r.z; o[4 * q + 3] = r.w;
+                    short* os = reinterpret_cast<short*>(o);
+                    const short p0 = to_pcm16(r.x), p1 = to_pcm16(r.y), p2 = to_pcm16(r.z), p3 = to_pcm16(r.w);
+                    if (o_vec) {
+                        reinterpret_cast<uint2*>(os)[q] = make_uint2((unsigned)(unsigned short)p0 | ((unsigned)(unsigned short)p1 << 16),
+                                                                     (unsigned)(unsigned short)p2 | ((unsigned)(unsigned short)p3 << 16));
+                    } else {
+                        os[4 * q] = p0; os[4 * q + 1] = p1; os[4 * q + 2] = p2; os[4 * q + 3] = p3;
+                    }
                 }
             } else {
                 reinterpret_cast<float4*>(fa_)[q - FRAME_SIZE / 4] = v;  // staged: sm is still being read by other threads
@@ -554,9 +571,10 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
     if (tid == 0 && vad_out) vad_out[s] = silent ? 0.0f : vad_in;
 }
 
-cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, float* out, long stream_stride, float* vad_out,
+cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride, float* vad_out,
                              cudaStream_t st) {
-    synthesis_kernel<<<b.n_streams, ST, 0, st>>>(b, tab, out, stream_stride, vad_out);
+    if (pcm16) synthesis_kernel<short><<<b.n_streams, ST, 0, st>>>(b, tab, static_cast<short*>(out), stream_stride, vad_out);
+    else synthesis_kernel<float><<<b.n_streams, ST, 0, st>>>(b, tab, static_cast<float*>(out), stream_stride, vad_out);
     return cudaGetLastError();
 }
 

@@ -301,3 +301,24 @@ def test_fp32_gru_kernel_agrees_with_tensor_core_kernel(builtin_bytes):
         del os.environ["NNB_RNN_FP32"]
     o_fp, v_fp = f.process_host(x)
     assert rel_rms(o_tc, o_fp) <= OUT_REL_RMS and np.abs(v_tc - v_fp).max() <= VAD_ATOL
+
+
+def test_pcm16_device_api_fused(builtin_bytes):
+    """int16 device buffers straight into the first kernel and out of the last one (N1 front-end, fused)."""
+    import torch
+    B, T = 33, 9
+    x = synth_streams(B, T, seed=91).reshape(B, T, 480)
+    ref = oracle_run(builtin_bytes, x)
+    xi = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 0, 2)).astype(np.int16)).cuda()   # [T][B][480]
+    oi = torch.empty_like(xi)
+    vad = torch.empty(T, B, device="cuda")
+    b = nb.DenoiseBatch(B)
+    b.process_device(oi.data_ptr(), xi.data_ptr(), vad.data_ptr(), T, 480, B * 480, torch.cuda.current_stream().cuda_stream, pcm16=True)
+    torch.cuda.synchronize()
+    want = np.clip(np.rint(ref["out"].transpose(1, 0, 2)), -32768, 32767).astype(np.int16)
+    got = oi.cpu().numpy()
+    assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1 and (got != want).mean() < 1e-2
+    assert np.abs(vad.cpu().numpy() - ref["vad"].T).max() <= VAD_ATOL
+    # and identical to the host pcm16 entry point
+    o16, _ = nb.DenoiseBatch(B).process_pcm16_host(xi.cpu().numpy())
+    assert np.array_equal(o16, got)

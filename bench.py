@@ -266,7 +266,11 @@ def run_b200(args):
     path_gbs = BYTES_PER_FRAME * B / (step_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
-        "achieved": path_gbs, "frac": path_gbs / peak, "traffic": None,
+        "achieved": path_gbs, "frac": path_gbs / peak,
+        # DRAM bytes per frame-step measured with ncu --set full (profiles/r01_v6_ncu_raw_B65536.csv: dram__bytes_read +
+        # dram__bytes_write of the five kernels = 2.40 GB at B = 65,536 = 36,600 B per stream-frame), scaled to this B
+        "traffic": 36600.0 * B, "traffic_unit": "bytes per frame-step (ncu, scaled from B=65536)",
+        "dominant_kernel_traffic": {"kernel": "pitch", "bytes_per_launch": 6982.0 * B, "algorithmic_bytes_per_launch": KERNEL_BYTES["pitch"] * B},
         "definition": "16,860 algorithmic B/frame (T=1: 3,844 I/O + 13,016 state round trip, SURVEY 8(d)) x %d frames "
                       "per frame-step / sum of the 5 kernels' CUDA-event durations" % B,
         "frame_step_ms": step_ms, "dominant_kernel": dom,
@@ -278,7 +282,9 @@ def run_b200(args):
     }
 
     # ---- e2e: same metric through the public host-buffer API (pinned host memory, copies inside the timed region) ----
-    Te = min(T, args.e2e_frames)
+    Te = min(T, args.e2e_frames) if args.e2e_frames > 0 else T
+    while Te > 1 and Te * B * FRAME * 4 > (2 << 30):  # keep each pinned staging buffer under 2 GiB
+        Te //= 2
     hx = torch.empty(Te, B, FRAME, dtype=torch.float32).pin_memory()
     hx.copy_(x[:Te].cpu())
     ho = torch.empty(Te, B, FRAME, dtype=torch.float32).pin_memory()
@@ -365,7 +371,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (configs[1] = 4096)")
     ap.add_argument("--frames", type=int, default=100, help="frames per stream per step")
-    ap.add_argument("--e2e-frames", type=int, default=25, help="frames per host-API call in the e2e leg")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per host-API call in the e2e leg (0 = --frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -70,7 +70,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -230,12 +230,19 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    if rank == 0:
+        # nvidia-smi needs a moment to start: keep the GPU under the same load until the first sample has arrived
+        t_wait = time.time()
+        while sampler.proc is not None and os.path.getsize(sampler.path) == 0 and time.time() - t_wait < 5.0:
+            step()
+            torch.cuda.synchronize()
+    barrier()
     l0 = nb.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -263,21 +270,25 @@ def run_b200(args):
     step_ms = sum(kavg.values())
     dom = max(kavg, key=kavg.get)
     peak, peak_src = load_peaks()
-    path_gbs = BYTES_PER_FRAME * B / (step_ms * 1e-3) / 1e9
+    # one launch set = one frame of the rank's B streams; its device time inside the timed region (stages of
+    # consecutive frames overlap) is ms_total / (frames per rank) -- all ranks run the same schedule
+    launch_ms = ms_total / (T * args.steps)
+    path_gbs = BYTES_PER_FRAME * B / (launch_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
-        "achieved": path_gbs, "frac": path_gbs / peak,
+        "achieved": path_gbs, "frac": path_gbs / peak, "frame_step_ms_pipelined": launch_ms,
         # DRAM bytes per frame-step measured with ncu --set full (profiles/r01_v6_ncu_raw_B65536.csv: dram__bytes_read +
         # dram__bytes_write of the five kernels = 2.40 GB at B = 65,536 = 36,600 B per stream-frame), scaled to this B
         "traffic": 36600.0 * B, "traffic_unit": "bytes per frame-step (ncu, scaled from B=65536)",
         "dominant_kernel_traffic": {"kernel": "pitch", "bytes_per_launch": 6982.0 * B, "algorithmic_bytes_per_launch": KERNEL_BYTES["pitch"] * B},
-        "definition": "16,860 algorithmic B/frame (T=1: 3,844 I/O + 13,016 state round trip, SURVEY 8(d)) x %d frames "
-                      "per frame-step / sum of the 5 kernels' CUDA-event durations" % B,
-        "frame_step_ms": step_ms, "dominant_kernel": dom,
+        "definition": "16,860 algorithmic B/frame (T=1: 3,844 I/O + 13,016 state round trip, SURVEY 8(d)) x %d frames per "
+                      "frame-step / CUDA-event time per frame-step inside the timed region (the five kernels of a frame-step; "
+                      "kernels of up to 4 consecutive frames overlap on separate streams)" % B,
+        "frame_step_ms_serial_sum": step_ms, "dominant_kernel": dom,
         "kernels": {k: {"ms": v, "share": v / step_ms, "own_bytes_per_frame": KERNEL_BYTES.get(k),
                         "own_gbs": (KERNEL_BYTES.get(k, 0) * B / (v * 1e-3) / 1e9) if v > 0 else None}
                     for k, v in kavg.items()},
-        "io_only_frac": (BYTES_IO * B / (step_ms * 1e-3) / 1e9) / peak,
+        "io_only_frac": (BYTES_IO * B / (launch_ms * 1e-3) / 1e9) / peak,
         "compute_note": "path is FP32-issue/latency bound, not HBM bound (SURVEY 8(d)); frac is reported against HBM as asked",
     }
 

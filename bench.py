@@ -294,7 +294,7 @@ def run_b200(args):
 
     # ---- e2e: same metric through the public host-buffer API (pinned host memory, copies inside the timed region) ----
     Te = min(T, args.e2e_frames) if args.e2e_frames > 0 else T
-    while Te > 1 and Te * B * FRAME * 4 > (2 << 30):  # keep each pinned staging buffer under 2 GiB
+    while Te > 1 and Te * B * FRAME * 4 > (512 << 20):  # keep each pinned staging buffer under 512 MiB
         Te //= 2
     hx = torch.empty(Te, B, FRAME, dtype=torch.float32).pin_memory()
     hx.copy_(x[:Te].cpu())

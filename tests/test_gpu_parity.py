@@ -322,3 +322,27 @@ def test_pcm16_device_api_fused(builtin_bytes):
     # and identical to the host pcm16 entry point
     o16, _ = nb.DenoiseBatch(B).process_pcm16_host(xi.cpu().numpy())
     assert np.array_equal(o16, got)
+
+
+def test_handles_on_concurrent_host_threads(builtin_bytes):
+    """`DenoiseState: Send + Sync` (src/denoise.rs:125) restated: independent states may be driven from different host
+    threads at the same time; results equal the single-threaded run bit for bit."""
+    import threading
+    B, T = 24, 8
+    xs = [np.ascontiguousarray(synth_streams(B, T, seed=200 + i).reshape(B, T, 480).transpose(1, 0, 2)) for i in range(4)]
+    want = [nb.DenoiseBatch(B).process_host(x) for x in xs]
+    got = [None] * 4
+
+    def work(i):
+        b = nb.DenoiseBatch(B)
+        outs, vads = [], []
+        for t in range(T):
+            o, v = b.process_host(xs[i][t:t + 1])
+            outs.append(o); vads.append(v)
+        got[i] = (np.concatenate(outs), np.concatenate(vads))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in th: t.start()
+    for t in th: t.join()
+    for i in range(4):
+        assert np.array_equal(got[i][0], want[i][0]) and np.array_equal(got[i][1], want[i][1])

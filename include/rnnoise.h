@@ -100,6 +100,13 @@ int rnnoise_batch_process_device(RNNoiseBatch *b, float *out, const float *in, f
 int rnnoise_batch_process_device_pcm16(RNNoiseBatch *b, short *out, const short *in, float *vad, int n_frames,
                                        long stream_stride, long frame_stride, void *cuda_stream);
 
+/* General layout: sample (s, t, i) at ptr[s*stream_stride + t*frame_stride + i*sample_stride] (element strides;
+ * float samples, or int16 when pcm16 != 0).  Interleaved multi-channel audio, where every channel is its own stream
+ * (src/signal.rs:90-107, src/nnnoiseless.rs:301-330), is stream_stride = 1, sample_stride = n_channels,
+ * frame_stride = 480 * n_channels. */
+int rnnoise_batch_process_device_strided(RNNoiseBatch *b, void *out, const void *in, int pcm16, float *vad, int n_frames,
+                                         long stream_stride, long sample_stride, long frame_stride, void *cuda_stream);
+
 /* Same through HOST buffers: copies in -> device, runs, copies out/vad back, synchronises.
  * Layout [n_frames][n_streams][480] (frame-major), vad [n_frames][n_streams]. */
 int rnnoise_batch_process_host(RNNoiseBatch *b, float *out, const float *in, float *vad, int n_frames);

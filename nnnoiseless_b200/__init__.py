@@ -29,7 +29,8 @@ C_ABI_SYMBOLS = [
     "rnnoise_process_frame", "rnnoise_model_from_file", "rnnoise_model_free",
     "rnnoise_model_from_bytes", "rnnoise_model_from_text", "rnnoise_model_bytes",
     "rnnoise_batch_create", "rnnoise_batch_destroy", "rnnoise_batch_streams", "rnnoise_batch_reset",
-    "rnnoise_batch_process_device", "rnnoise_batch_process_device_pcm16", "rnnoise_batch_process_host",
+    "rnnoise_batch_process_device", "rnnoise_batch_process_device_pcm16", "rnnoise_batch_process_device_strided",
+    "rnnoise_batch_process_host",
     "rnnoise_batch_process_pcm16_host",
     "rnnoise_batch_get_taps", "rnnoise_batch_profile_step", "rnnoise_kernel_name",
     "rnnoise_kernel_launches", "rnnoise_last_error",
@@ -81,6 +82,8 @@ def lib():
     L.rnnoise_batch_process_device.argtypes = [vp, vp, vp, vp, ci, C.c_long, C.c_long, vp]
     L.rnnoise_batch_process_device_pcm16.restype = ci
     L.rnnoise_batch_process_device_pcm16.argtypes = [vp, vp, vp, vp, ci, C.c_long, C.c_long, vp]
+    L.rnnoise_batch_process_device_strided.restype = ci
+    L.rnnoise_batch_process_device_strided.argtypes = [vp, vp, vp, ci, vp, ci, C.c_long, C.c_long, C.c_long, vp]
     L.rnnoise_batch_process_host.restype = ci
     L.rnnoise_batch_process_host.argtypes = [vp, vp, vp, vp, ci]
     L.rnnoise_batch_process_pcm16_host.restype = ci

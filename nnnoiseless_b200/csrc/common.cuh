@@ -127,12 +127,13 @@ struct BatchBuffers {
 
 // ---- launchers (one per translation unit) ------------------------------------------------------
 // exact.cu (compiled with -fmad=false: bit-exact pitch path)
-cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, long stream_stride, int slot, cudaStream_t st);
+cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, long stream_stride, long sample_stride, int slot,
+                             cudaStream_t st);
 cudaError_t launch_pitch(const BatchBuffers& b, int slot, cudaStream_t st);
 // spectral.cu
 cudaError_t launch_analysis(const BatchBuffers& b, const DeviceTables* tab, int slot, cudaStream_t st);
-cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride, float* vad_out,
-                             cudaStream_t st);
+cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride, long sample_stride,
+                             float* vad_out, cudaStream_t st);
 // rnn.cu
 cudaError_t launch_rnn(const BatchBuffers& b, const DeviceModel& m, const DeviceTables* tab, cudaStream_t st);
 // rnn_mma.cu

@@ -30,7 +30,7 @@ static_assert(FRAME_SIZE % HP_CHUNK == 0 && HP_CHUNK % 4 == 0, "chunking must ti
 
 // TIn = float (the reference's f32-in-i16-range samples) or short (16-bit PCM, src/nnnoiseless.rs:147-177 front-end fused in)
 template <typename TIn>
-__global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const TIn* __restrict__ in, long stream_stride,
+__global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const TIn* __restrict__ in, long stream_stride, long sample_stride,
                                                                float* __restrict__ hist, float* __restrict__ hp_mem,
                                                                int n_streams, int slot, int vec_ok) {
     __shared__ float tile[HP_STREAMS * HP_LD];
@@ -65,10 +65,15 @@ __global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const TIn* __rest
                     t[2 * k + 1] = (float)(short)(w[k] >> 16);
                 }
             }
-        } else {
+        } else if (sample_stride == 1) {
             for (int idx = tid; idx < ns * HP_CHUNK; idx += HP_THREADS) {
                 const int row = idx / HP_CHUNK, i = idx - row * HP_CHUNK;
                 tile[row * HP_LD + i] = (float)in[(long)(s0 + row) * stream_stride + c * HP_CHUNK + i];
+            }
+        } else {  // interleaved channels: neighbouring threads take neighbouring streams of the same sample
+            for (int idx = tid; idx < ns * HP_CHUNK; idx += HP_THREADS) {
+                const int i = idx / ns, row = idx - i * ns;
+                tile[row * HP_LD + i] = (float)in[(long)(s0 + row) * stream_stride + (long)(c * HP_CHUNK + i) * sample_stride];
             }
         }
         __syncthreads();
@@ -101,14 +106,17 @@ __global__ void __launch_bounds__(HP_THREADS) hp_filter_kernel(const TIn* __rest
     }
 }
 
-cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, long stream_stride, int slot, cudaStream_t st) {
+cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, long stream_stride, long sample_stride, int slot,
+                             cudaStream_t st) {
     const int per16 = pcm16 ? 8 : 4;  // elements per 128-bit load
-    int vec_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (stream_stride % per16 == 0);
+    int vec_ok = sample_stride == 1 && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (stream_stride % per16 == 0);
     int grid = (b.n_streams + HP_STREAMS - 1) / HP_STREAMS;
     if (pcm16)
-        hp_filter_kernel<short><<<grid, HP_THREADS, 0, st>>>(static_cast<const short*>(in), stream_stride, b.hist, b.hp_mem, b.n_streams, slot, vec_ok);
+        hp_filter_kernel<short><<<grid, HP_THREADS, 0, st>>>(static_cast<const short*>(in), stream_stride, sample_stride, b.hist, b.hp_mem,
+                                                             b.n_streams, slot, vec_ok);
     else
-        hp_filter_kernel<float><<<grid, HP_THREADS, 0, st>>>(static_cast<const float*>(in), stream_stride, b.hist, b.hp_mem, b.n_streams, slot, vec_ok);
+        hp_filter_kernel<float><<<grid, HP_THREADS, 0, st>>>(static_cast<const float*>(in), stream_stride, sample_stride, b.hist, b.hp_mem,
+                                                             b.n_streams, slot, vec_ok);
     return cudaGetLastError();
 }
 

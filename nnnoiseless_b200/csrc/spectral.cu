@@ -408,7 +408,7 @@ __device__ __forceinline__ short to_pcm16(float v) { return (short)roundf(fminf(
 
 template <typename TOut>
 __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab,
-                                                       TOut* __restrict__ out, long stream_stride,
+                                                       TOut* __restrict__ out, long stream_stride, long sample_stride,
                                                        float* __restrict__ vad_out) {
     __shared__ __align__(16) float2 xs[FREQ_SIZE + 1];
     __shared__ __align__(16) float2 fa_[480];
@@ -533,7 +533,8 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
     TOut* o = out + (long)s * stream_stride;
     // time samples 4q..4q+3 = (re, -im) of fb_[2q], fb_[2q+1]; first half -> output (+ overlap memory),
     // second half -> new overlap memory.  Vector stores when the caller's rows are aligned for them.
-    const bool o_vec = ((reinterpret_cast<uintptr_t>(o) & (4 * sizeof(TOut) - 1)) == 0);
+    const bool o_vec = sample_stride == 1 && ((reinterpret_cast<uintptr_t>(o) & (4 * sizeof(TOut) - 1)) == 0);
+    const long ss = sample_stride;
 #pragma unroll
     for (int it = 0; it < 2; it++) {
         const int q = tid + it * ST;
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
                     if (o_vec) {
                         reinterpret_cast<float4*>(of)[q] = r;
                     } else {
-                        of[4 * q] = r.x; of[4 * q + 1] = r.y; of[4 * q + 2] = r.z; of[4 * q + 3] = r.w;
+                        of[(4 * q) * ss] = r.x; of[(4 * q + 1) * ss] = r.y; of[(4 * q + 2) * ss] = r.z; of[(4 * q + 3) * ss] = r.w;
                     }
                 } else {
                     short* os = reinterpret_cast<short*>(o);
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
                         reinterpret_cast<uint2*>(os)[q] = make_uint2((unsigned)(unsigned short)p0 | ((unsigned)(unsigned short)p1 << 16),
                                                                      (unsigned)(unsigned short)p2 | ((unsigned)(unsigned short)p3 << 16));
                     } else {
-                        os[4 * q] = p0; os[4 * q + 1] = p1; os[4 * q + 2] = p2; os[4 * q + 3] = p3;
+                        os[(4 * q) * ss] = p0; os[(4 * q + 1) * ss] = p1; os[(4 * q + 2) * ss] = p2; os[(4 * q + 3) * ss] = p3;
                     }
                 }
             } else {
@@ -571,10 +572,10 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
     if (tid == 0 && vad_out) vad_out[s] = silent ? 0.0f : vad_in;
 }
 
-cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride, float* vad_out,
-                             cudaStream_t st) {
-    if (pcm16) synthesis_kernel<short><<<b.n_streams, ST, 0, st>>>(b, tab, static_cast<short*>(out), stream_stride, vad_out);
-    else synthesis_kernel<float><<<b.n_streams, ST, 0, st>>>(b, tab, static_cast<float*>(out), stream_stride, vad_out);
+cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride, long sample_stride,
+                             float* vad_out, cudaStream_t st) {
+    if (pcm16) synthesis_kernel<short><<<b.n_streams, ST, 0, st>>>(b, tab, static_cast<short*>(out), stream_stride, sample_stride, vad_out);
+    else synthesis_kernel<float><<<b.n_streams, ST, 0, st>>>(b, tab, static_cast<float*>(out), stream_stride, sample_stride, vad_out);
     return cudaGetLastError();
 }
 

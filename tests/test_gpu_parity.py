@@ -346,3 +346,29 @@ def test_handles_on_concurrent_host_threads(builtin_bytes):
     for t in th: t.join()
     for i in range(4):
         assert np.array_equal(got[i][0], want[i][0]) and np.array_equal(got[i][1], want[i][1])
+
+
+def test_interleaved_channels_layout(builtin_bytes):
+    """Multi-channel interleaved audio, every channel its own stream (src/signal.rs:90-107, src/nnnoiseless.rs:301-330):
+    sample (channel c, frame t, i) at [t*480*C + i*C + c].  Same bits as the planar layout, float and int16."""
+    import ctypes as C
+    import torch
+    Cn, T = 6, 7
+    x = np.ascontiguousarray(synth_streams(Cn, T, seed=55).reshape(Cn, T, 480).transpose(1, 0, 2))   # planar [T][C][480]
+    o_ref, v_ref = nb.DenoiseBatch(Cn).process_host(x)
+    xi = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 1))).cuda()                            # [T][480][C]
+    oi = torch.empty_like(xi)
+    vad = torch.empty(T, Cn, device="cuda")
+    b = nb.DenoiseBatch(Cn)
+    rc = nb.lib().rnnoise_batch_process_device_strided(b._h, C.c_void_p(oi.data_ptr()), C.c_void_p(xi.data_ptr()), 0,
+                                                       C.c_void_p(vad.data_ptr()), T, 1, Cn, 480 * Cn, None)
+    assert rc == 0, nb.last_error()
+    assert np.array_equal(oi.cpu().numpy().transpose(0, 2, 1), o_ref) and np.array_equal(vad.cpu().numpy(), v_ref)
+    # int16, in place
+    x16 = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 1)).astype(np.int16)).cuda()
+    b2 = nb.DenoiseBatch(Cn)
+    rc = nb.lib().rnnoise_batch_process_device_strided(b2._h, C.c_void_p(x16.data_ptr()), C.c_void_p(x16.data_ptr()), 1,
+                                                       None, T, 1, Cn, 480 * Cn, None)
+    assert rc == 0, nb.last_error()
+    want, _ = nb.DenoiseBatch(Cn).process_pcm16_host(x.astype(np.int16))
+    assert np.array_equal(x16.cpu().numpy().transpose(0, 2, 1), want)

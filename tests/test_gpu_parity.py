@@ -372,3 +372,24 @@ def test_interleaved_channels_layout(builtin_bytes):
     assert rc == 0, nb.last_error()
     want, _ = nb.DenoiseBatch(Cn).process_pcm16_host(x.astype(np.int16))
     assert np.array_equal(x16.cpu().numpy().transpose(0, 2, 1), want)
+
+
+def test_long_run_no_drift(builtin_bytes):
+    """6 s of audio (600 frames) per stream: the recurrent state (GRU, cepstral ring, pitch continuity, overlap-add)
+    must not drift away from the oracle over time; the pitch period stays exact on every one of the 2,400 frames."""
+    B, T = 4, 600
+    x = synth_streams(B, T, seed=123).reshape(B, T, 480)
+    ref = oracle_run(builtin_bytes, x)
+    b = nb.DenoiseBatch(B)
+    xt = np.ascontiguousarray(x.transpose(1, 0, 2))
+    outs, vads, pitches = [], [], []
+    for t0 in range(0, T, 50):
+        for t in range(t0, t0 + 50):
+            o, v = b.process_host(xt[t:t + 1])
+            outs.append(o[0]); vads.append(v[0]); pitches.append(b.taps()["pitch"].copy())
+    o, v = np.stack(outs), np.stack(vads)
+    assert np.array_equal(np.stack(pitches, 1), ref["pitch"])
+    o_ref = ref["out"].transpose(1, 0, 2)
+    assert rel_rms(o, o_ref) <= OUT_REL_RMS
+    assert rel_rms(o[-100:], o_ref[-100:]) <= OUT_REL_RMS          # the last second is as good as the first
+    assert np.abs(v - ref["vad"].T).max() <= VAD_ATOL

@@ -129,6 +129,37 @@ int rnnoise_batch_profile_step(RNNoiseBatch *b, float *out, const float *in, flo
                                void *cuda_stream, float *ms, int cap);
 const char *rnnoise_kernel_name(int i);
 
+/* ---- training-data rows on the GPU (additive; the arithmetic of the reference's `nnnoiseless-gen-training-data`
+ * binary, src/training.rs:113-161 main loop + :399-432 NoiseSimulator::next_frame) ------------------------------
+ * A lane is one NoiseSimulator with its three DenoiseFeatures (clean, noise, combined).  File reading and the random
+ * draws of NoiseSimulator::randomize (:352-377) stay with the caller, who passes their outcome as RNNoiseSimParams
+ * (initially NoiseSimulator::new: gains 1, zero filters, band_lp 21) and may change it between calls.  Per frame and
+ * lane the library consumes one raw 480-sample signal frame and one noise frame (i16-valued floats as
+ * SignalReader::frame yields them, :237-262) and produces the 87-float row
+ *   [42 features of the combined signal | 22 band gains (-1 = masked) | 22 log10 noise levels | vad]. */
+#define RNNOISE_TRAIN_ROW 87
+typedef struct RNNoiseSimParams {
+    float signal_gain, noise_gain;     /* NoiseSimulator::{signal_gain, noise_gain} */
+    float sig_a[2], sig_b[2];          /* sig_filter (Biquad {a, b}, src/util.rs:82-93) */
+    float noise_a[2], noise_b[2];      /* noise_filter */
+    int band_lp;                       /* NoiseSimulator::band_lp */
+} RNNoiseSimParams;
+typedef struct RNNoiseTrainer RNNoiseTrainer;
+RNNoiseTrainer *rnnoise_train_create(int n_lanes, int device);      /* NULL on error */
+void rnnoise_train_destroy(RNNoiseTrainer *t);
+int rnnoise_train_lanes(const RNNoiseTrainer *t);
+int rnnoise_train_set_params(RNNoiseTrainer *t, int first_lane, int n, const RNNoiseSimParams *params);
+/* EBAND_5MS.position(|x| x << 2 > lowpass).unwrap_or(21), src/training.rs:373-376 */
+int rnnoise_train_band_lp(int lowpass);
+/* HOST buffers: signal, noise [n_frames][n_lanes][480]; rows [n_frames][n_lanes][87]. */
+int rnnoise_train_process_host(RNNoiseTrainer *t, float *rows, const float *signal, const float *noise, int n_frames);
+/* DEVICE buffers: signal/noise sample (l, f, i) at ptr[l*stream_stride + f*frame_stride + i]; row (l, f) at
+ * rows[l*row_lane_stride + f*row_frame_stride].  Asynchronous with respect to the host like
+ * rnnoise_batch_process_device (cuda_stream NULL: synchronises before returning). */
+int rnnoise_train_process_device(RNNoiseTrainer *t, float *rows, const float *signal, const float *noise, int n_frames,
+                                 long stream_stride, long frame_stride, long row_lane_stride, long row_frame_stride,
+                                 void *cuda_stream);
+
 /* Number of kernel launches issued by this library since load (bench evidence). */
 unsigned long long rnnoise_kernel_launches(void);
 

@@ -33,6 +33,8 @@ C_ABI_SYMBOLS = [
     "rnnoise_batch_process_host",
     "rnnoise_batch_process_pcm16_host",
     "rnnoise_batch_get_taps", "rnnoise_batch_profile_step", "rnnoise_kernel_name",
+    "rnnoise_train_create", "rnnoise_train_destroy", "rnnoise_train_lanes", "rnnoise_train_set_params",
+    "rnnoise_train_band_lp", "rnnoise_train_process_host", "rnnoise_train_process_device",
     "rnnoise_kernel_launches", "rnnoise_last_error",
 ]
 
@@ -92,6 +94,19 @@ def lib():
     L.rnnoise_batch_get_taps.argtypes = [vp, vp, vp, vp, vp]
     L.rnnoise_batch_profile_step.restype = ci
     L.rnnoise_batch_profile_step.argtypes = [vp, vp, vp, vp, C.c_long, vp, vp, ci]
+    L.rnnoise_train_create.restype = vp
+    L.rnnoise_train_create.argtypes = [ci, ci]
+    L.rnnoise_train_destroy.argtypes = [vp]
+    L.rnnoise_train_lanes.restype = ci
+    L.rnnoise_train_lanes.argtypes = [vp]
+    L.rnnoise_train_set_params.restype = ci
+    L.rnnoise_train_set_params.argtypes = [vp, ci, ci, vp]
+    L.rnnoise_train_band_lp.restype = ci
+    L.rnnoise_train_band_lp.argtypes = [ci]
+    L.rnnoise_train_process_host.restype = ci
+    L.rnnoise_train_process_host.argtypes = [vp, vp, vp, vp, ci]
+    L.rnnoise_train_process_device.restype = ci
+    L.rnnoise_train_process_device.argtypes = [vp, vp, vp, vp, ci, C.c_long, C.c_long, C.c_long, C.c_long, vp]
     L.rnnoise_kernel_name.restype = C.c_char_p
     L.rnnoise_kernel_name.argtypes = [ci]
     L.rnnoise_kernel_launches.restype = C.c_ulonglong

@@ -23,6 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 UNITS = [
     ("exact.cu", ["-fmad=false"]),
     ("pitch.cu", ["-fmad=false"]),
+    ("train.cu", ["-fmad=false"]),
     ("spectral.cu", []),
     ("rnn.cu", ["-DRNN_RT=256", "-DRNN_UNROLL=8"]),
     ("rnn_mma.cu", []),

@@ -125,6 +125,22 @@ struct BatchBuffers {
     float* vad;          // [B]
 };
 
+// ---- training-data rows (src/training.rs): per-lane simulator parameters and state --------------------
+constexpr int TRAIN_ROW = NB_FEATURES + 2 * NB_BANDS + 1;  // 87, src/training.rs:90
+struct TrainLaneParams {  // == RNNoiseSimParams (include/rnnoise.h)
+    float signal_gain, noise_gain;
+    float sig_a[2], sig_b[2], noise_a[2], noise_b[2];
+    int32_t band_lp;
+};
+struct TrainBuffers {
+    int n_lanes;
+    TrainLaneParams* params;  // [L]
+    float* resp_mem;          // [L][4]  signal_resp_mem | noise_resp_mem
+    int32_t* vad_count;       // [L]
+    float* vad;               // [PIPE_DEPTH][L]
+    int32_t* cutoff;          // [PIPE_DEPTH][L]  band_gain_cutoff before the silence override
+};
+
 // ---- launchers (one per translation unit) ------------------------------------------------------
 // exact.cu (compiled with -fmad=false: bit-exact pitch path)
 cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, long stream_stride, long sample_stride, int slot,
@@ -138,5 +154,10 @@ cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, voi
 cudaError_t launch_rnn(const BatchBuffers& b, const DeviceModel& m, const DeviceTables* tab, cudaStream_t st);
 // rnn_mma.cu
 cudaError_t launch_rnn_mma(const BatchBuffers& b, const DeviceModelMma& m, const DeviceTables* tab, cudaStream_t st);
+
+// train.cu (-fmad=false)
+cudaError_t launch_train_front(const BatchBuffers& b, const TrainBuffers& tb, int set, const float* signal, const float* noise,
+                               long stream_stride, int slot, cudaStream_t st);
+cudaError_t launch_train_rows(const BatchBuffers& b, const TrainBuffers& tb, int set, float* rows, long lane_stride, cudaStream_t st);
 
 }  // namespace nnb

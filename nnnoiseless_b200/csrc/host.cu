@@ -797,6 +797,202 @@ int rnnoise_batch_get_taps(RNNoiseBatch* b, int* pitch, int* silence, float* fea
     return 0;
 }
 
+}  // extern "C"
+
+// ---- training-data rows (src/training.rs): 3 feature extractors per lane on the denoise path's kernels ----------
+static_assert(sizeof(RNNoiseSimParams) == sizeof(TrainLaneParams), "C ABI struct and device struct must match");
+constexpr int kTrainStages = 4;  // front, pitch, analysis, rows
+
+struct RNNoiseTrainer {
+    RNNoiseBatch* batch = nullptr;  // 3 * n_lanes streams: [0, L) clean, [L, 2L) noise, [2L, 3L) combined
+    TrainBuffers tb{};
+    float* stage_sig = nullptr;
+    float* stage_noise = nullptr;
+    float* stage_rows = nullptr;
+    int stage_frames = 0;
+};
+
+namespace {
+
+void trainer_release(RNNoiseTrainer* t) {
+    if (!t) return;
+    if (t->batch) {
+        cudaSetDevice(t->batch->device);
+        sync_all(t->batch);
+    }
+    cudaFree(t->tb.params);
+    cudaFree(t->tb.resp_mem);
+    cudaFree(t->tb.vad_count);
+    cudaFree(t->tb.vad);
+    cudaFree(t->tb.cutoff);
+    cudaFree(t->stage_sig);
+    cudaFree(t->stage_noise);
+    cudaFree(t->stage_rows);
+    if (t->batch) rnnoise_batch_destroy(t->batch);
+    delete t;
+}
+
+int trainer_init(RNNoiseTrainer* t, int n_lanes) {
+    const size_t L = (size_t)n_lanes;
+    TrainBuffers& tb = t->tb;
+    tb.n_lanes = n_lanes;
+    CK(cudaMalloc(&tb.params, L * sizeof(TrainLaneParams)));
+    CK(cudaMalloc(&tb.resp_mem, L * 4 * sizeof(float)));
+    CK(cudaMalloc(&tb.vad_count, L * sizeof(int32_t)));
+    CK(cudaMalloc(&tb.vad, PIPE_DEPTH * L * sizeof(float)));
+    CK(cudaMalloc(&tb.cutoff, PIPE_DEPTH * L * sizeof(int32_t)));
+    CK(cudaMemset(tb.resp_mem, 0, L * 4 * sizeof(float)));
+    CK(cudaMemset(tb.vad_count, 0, L * sizeof(int32_t)));
+    TrainLaneParams d{};  // NoiseSimulator::new, src/training.rs:319-340
+    d.signal_gain = 1.0f;
+    d.noise_gain = 1.0f;
+    d.band_lp = NB_BANDS - 1;
+    std::vector<TrainLaneParams> init(L, d);
+    CK(cudaMemcpy(tb.params, init.data(), L * sizeof(TrainLaneParams), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// One frame of every lane: front -> pitch -> analysis -> rows on the batch's first four stage streams (same event
+// scheme as step_pipelined; the rows kernel is the last stage).
+int train_step(RNNoiseTrainer* t, float* rows, long row_lane_stride, const float* sig, const float* noise, long stream_stride,
+               cudaEvent_t in_ready) {
+    RNNoiseBatch* b = t->batch;
+    const unsigned long long f = b->frame;
+    const int slot = (int)(f % HIST_SLOTS), e = (int)(f % kEvRing), set = (int)(f % PIPE_DEPTH);
+    const BatchBuffers v = view(b, f);
+    cudaStream_t s0 = b->serial ? b->st[0] : nullptr;
+    auto S = [&](int i) { return s0 ? s0 : b->st[i]; };
+    if (in_ready) CK(cudaStreamWaitEvent(S(0), in_ready, 0));
+    if (!s0 && f >= (unsigned long long)PIPE_DEPTH) CK(cudaStreamWaitEvent(S(0), b->ev[kTrainStages - 1][(int)((f - PIPE_DEPTH) % kEvRing)], 0));
+    for (int i = 0; i < kTrainStages; i++) {
+        if (!s0 && i > 0) CK(cudaStreamWaitEvent(S(i), b->ev[i - 1][e], 0));
+        switch (i) {
+            case 0: CK(launch_train_front(v, t->tb, set, sig, noise, stream_stride, slot, S(i))); break;
+            case 1: CK(launch_pitch(v, slot, S(i))); break;
+            case 2: CK(launch_analysis(v, b->d_tab, slot, S(i))); break;
+            default: CK(launch_train_rows(v, t->tb, set, rows, row_lane_stride, S(i))); break;
+        }
+        CK(cudaEventRecord(b->ev[i][e], S(i)));
+    }
+    g_launches.fetch_add(kTrainStages, std::memory_order_relaxed);
+    b->frame++;
+    return 0;
+}
+
+int train_join(RNNoiseTrainer* t, cudaStream_t s) {
+    RNNoiseBatch* b = t->batch;
+    if (b->frame == 0) return 0;
+    CK(cudaStreamWaitEvent(s, b->ev[kTrainStages - 1][(int)((b->frame - 1) % kEvRing)], 0));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+RNNoiseTrainer* rnnoise_train_create(int n_lanes, int device) {
+    if (n_lanes <= 0 || n_lanes > (1 << 29) / 3) {
+        fail("n_lanes out of range");
+        return nullptr;
+    }
+    RNNoiseTrainer* t = new (std::nothrow) RNNoiseTrainer();
+    if (!t) return nullptr;
+    t->batch = rnnoise_batch_create(nullptr, 3 * n_lanes, device);
+    if (!t->batch || trainer_init(t, n_lanes) != 0) {
+        std::string keep = g_err;
+        trainer_release(t);
+        g_err = keep;
+        return nullptr;
+    }
+    return t;
+}
+
+void rnnoise_train_destroy(RNNoiseTrainer* t) { trainer_release(t); }
+int rnnoise_train_lanes(const RNNoiseTrainer* t) { return t ? t->tb.n_lanes : 0; }
+
+int rnnoise_train_band_lp(int lowpass) {
+    static const int eband[NB_BANDS] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 34, 40, 48, 60, 78, 100};  // src/lib.rs:55-58
+    for (int i = 0; i < NB_BANDS; i++)
+        if ((eband[i] << 2) > lowpass) return i;
+    return NB_BANDS - 1;
+}
+
+int rnnoise_train_set_params(RNNoiseTrainer* t, int first_lane, int n, const RNNoiseSimParams* params) {
+    if (!t || !params) return fail("null argument");
+    if (first_lane < 0 || n < 0 || first_lane + n > t->tb.n_lanes) return fail("lane range out of bounds");
+    for (int i = 0; i < n; i++)
+        if (params[i].band_lp < 0 || params[i].band_lp >= NB_BANDS) return fail("band_lp must be in [0, 21]");
+    CK(cudaSetDevice(t->batch->device));
+    if (sync_all(t->batch)) return -1;  // frames in flight still read the old parameters
+    CK(cudaMemcpy(t->tb.params + first_lane, params, (size_t)n * sizeof(TrainLaneParams), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int rnnoise_train_process_device(RNNoiseTrainer* t, float* rows, const float* signal, const float* noise, int n_frames, long stream_stride,
+                                 long frame_stride, long row_lane_stride, long row_frame_stride, void* cuda_stream) {
+    if (!t || !rows || !signal || !noise) return fail("null argument");
+    if (n_frames < 0) return fail("negative n_frames");
+    if (n_frames == 0) return 0;
+    RNNoiseBatch* b = t->batch;
+    CK(cudaSetDevice(b->device));
+    cudaStream_t us = (cudaStream_t)cuda_stream;
+    cudaEvent_t ready = nullptr;
+    if (us) {
+        CK(cudaEventRecord(b->ev_call, us));
+        ready = b->ev_call;
+    }
+    for (int f = 0; f < n_frames; f++)
+        if (train_step(t, rows + (size_t)f * row_frame_stride, row_lane_stride, signal + (size_t)f * frame_stride,
+                       noise + (size_t)f * frame_stride, stream_stride, f == 0 ? ready : nullptr))
+            return -1;
+    cudaStream_t last = b->serial ? b->st[0] : b->st[kTrainStages - 1];
+    if (us) {
+        if (train_join(t, us)) return -1;
+    } else {
+        CK(cudaStreamSynchronize(last));
+    }
+    return 0;
+}
+
+int rnnoise_train_process_host(RNNoiseTrainer* t, float* rows, const float* signal, const float* noise, int n_frames) {
+    if (!t || !rows || !signal || !noise) return fail("null argument");
+    if (n_frames < 0) return fail("negative n_frames");
+    if (n_frames == 0) return 0;
+    RNNoiseBatch* b = t->batch;
+    CK(cudaSetDevice(b->device));
+    const size_t L = (size_t)t->tb.n_lanes;
+    // staging is bounded (<= 256 MiB per input buffer): long runs go through in chunks of frames
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_frames, (size_t(256) << 20) / (L * FRAME_SIZE * sizeof(float))));
+    if (chunk > t->stage_frames) {
+        if (sync_all(b)) return -1;
+        cudaFree(t->stage_sig);
+        cudaFree(t->stage_noise);
+        cudaFree(t->stage_rows);
+        t->stage_sig = t->stage_noise = t->stage_rows = nullptr;
+        t->stage_frames = 0;
+        CK(cudaMalloc(&t->stage_sig, (size_t)chunk * L * FRAME_SIZE * sizeof(float)));
+        CK(cudaMalloc(&t->stage_noise, (size_t)chunk * L * FRAME_SIZE * sizeof(float)));
+        CK(cudaMalloc(&t->stage_rows, (size_t)chunk * L * TRAIN_ROW * sizeof(float)));
+        t->stage_frames = chunk;
+    }
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = std::min(chunk, n_frames - f0);
+        const size_t off = (size_t)f0 * L;
+        CK(cudaMemcpyAsync(t->stage_sig, signal + off * FRAME_SIZE, (size_t)nf * L * FRAME_SIZE * sizeof(float), cudaMemcpyHostToDevice, b->c_in));
+        CK(cudaMemcpyAsync(t->stage_noise, noise + off * FRAME_SIZE, (size_t)nf * L * FRAME_SIZE * sizeof(float), cudaMemcpyHostToDevice, b->c_in));
+        if (rnnoise_train_process_device(t, t->stage_rows, t->stage_sig, t->stage_noise, nf, FRAME_SIZE, (long)(L * FRAME_SIZE), TRAIN_ROW,
+                                         (long)(L * TRAIN_ROW), b->c_in))
+            return -1;
+        CK(cudaMemcpyAsync(rows + off * TRAIN_ROW, t->stage_rows, (size_t)nf * L * TRAIN_ROW * sizeof(float), cudaMemcpyDeviceToHost, b->c_in));
+        CK(cudaStreamSynchronize(b->c_in));
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
 // ---- legacy single-stream API (src/capi.rs) = a batch of one ------------------------------------------
 struct DenoiseState {
     RNNoiseBatch* batch;

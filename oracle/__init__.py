@@ -90,6 +90,12 @@ def lib():
         L.nno_run_batch.restype = C.c_double
         L.nno_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.nno_train_new.restype = C.c_void_p
+        L.nno_train_free.argtypes = [C.c_void_p]
+        L.nno_train_set_params.argtypes = [C.c_void_p, C.c_void_p]
+        L.nno_train_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nno_train_band_lp.restype = C.c_int32
+        L.nno_train_band_lp.argtypes = [C.c_int32]
         _lib = L
     return _lib
 
@@ -177,3 +183,33 @@ def run_batch(model: Model, x: np.ndarray, n_threads=0, want_out=True, want_taps
     used = C.c_int(0)
     secs = lib().nno_run_batch(model._h, _ptr(x), _ptr(out), _ptr(vad), _ptr(pitch), B, T, n_threads, C.byref(used))
     return dict(out=out, vad=vad, pitch=pitch, seconds=float(secs), threads=int(used.value))
+
+
+class Trainer:
+    """One lane of the training-data generator (src/training.rs main loop + NoiseSimulator::next_frame)."""
+
+    def __init__(self):
+        self._h = lib().nno_train_new()
+
+    def set_params(self, params44: np.ndarray):
+        """params44: one record laid out like nno_sim_params (44 bytes)."""
+        buf = np.ascontiguousarray(params44)
+        assert buf.nbytes == 44
+        lib().nno_train_set_params(self._h, _ptr(buf))
+
+    def frame(self, signal, noise):
+        signal = np.ascontiguousarray(signal, dtype=np.float32)
+        noise = np.ascontiguousarray(noise, dtype=np.float32)
+        assert signal.shape == (FRAME_SIZE,) and noise.shape == (FRAME_SIZE,)
+        row = np.empty(87, np.float32)
+        lib().nno_train_frame(self._h, _ptr(signal), _ptr(noise), _ptr(row))
+        return row
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().nno_train_free(self._h)
+            self._h = None
+
+
+def train_band_lp(lowpass: int) -> int:
+    return int(lib().nno_train_band_lp(int(lowpass)))

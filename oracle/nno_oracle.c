@@ -929,3 +929,102 @@ double nno_run_batch(const nno_model *m, const float *in, float *out, float *vad
     if (threads_used) *threads_used = used;
     return t1 - t0;
 }
+
+/* ---- training-data rows: src/training.rs ---------------------------------------------------- */
+/* Biquad::filter_in_place, src/util.rs:113-124 (f64 arithmetic, f32 state) */
+static void biquad_in_place(const float a[2], const float b[2], float *data, float mem[2], int n) {
+    const double a0 = (double)a[0], a1 = (double)a[1], b0 = (double)b[0], b1 = (double)b[1];
+    for (int i = 0; i < n; i++) {
+        double x64 = (double)data[i];
+        double y64 = x64 + (double)mem[0];
+        mem[0] = (float)((double)mem[1] + (b0 * x64 - a0 * y64));
+        mem[1] = (float)(b1 * x64 - a1 * y64);
+        data[i] = (float)y64;
+    }
+}
+
+struct nno_trainer {
+    nno_sim_params p;
+    int vad_count;                              /* NoiseSimulator::vad_count, src/training.rs:288 */
+    float signal_resp_mem[2], noise_resp_mem[2]; /* :299-300 */
+    nno_state *clean, *noise, *comb;            /* src/training.rs:113-115 */
+};
+
+nno_trainer *nno_train_new(void) {
+    nno_trainer *t = (nno_trainer *)calloc(1, sizeof(*t));
+    if (!t) return NULL;
+    /* NoiseSimulator::new, src/training.rs:319-340 */
+    t->p.signal_gain = 1.0f;
+    t->p.noise_gain = 1.0f;
+    t->p.band_lp = NB_BANDS - 1;
+    t->clean = nno_state_new(NULL);
+    t->noise = nno_state_new(NULL);
+    t->comb = nno_state_new(NULL);
+    return t;
+}
+
+void nno_train_free(nno_trainer *t) {
+    if (!t) return;
+    nno_state_free(t->clean);
+    nno_state_free(t->noise);
+    nno_state_free(t->comb);
+    free(t);
+}
+
+void nno_train_set_params(nno_trainer *t, const nno_sim_params *p) { t->p = *p; }
+
+int32_t nno_train_band_lp(int32_t lowpass) {
+    for (int i = 0; i < NB_BANDS; i++)
+        if ((EBAND_5MS[i] << 2) > lowpass) return i;
+    return NB_BANDS - 1;
+}
+
+/* DenoiseFeatures::shift_and_filter_input, src/features.rs:97-104 */
+static void shift_and_filter(nno_state *s, const float *in) {
+    memmove(s->input_mem, s->input_mem + FRAME_SIZE, (PITCH_BUF_SIZE - FRAME_SIZE) * sizeof(float));
+    biquad_hp(s->input_mem + (PITCH_BUF_SIZE - FRAME_SIZE), s->mem_hp_x, in, FRAME_SIZE);
+}
+
+void nno_train_frame(nno_trainer *t, const float *signal, const float *noise, float *row) {
+    float sig_buf[FRAME_SIZE], noise_buf[FRAME_SIZE], out_buf[FRAME_SIZE];
+    /* NoiseSimulator::next_frame, src/training.rs:399-432 (the randomize() trigger is the caller's) */
+    for (int i = 0; i < FRAME_SIZE; i++) noise_buf[i] = noise[i] * t->p.noise_gain; /* read_noise :342-348 */
+    float sig_e = 0.0f;                                                            /* read_signal :351-359 */
+    for (int i = 0; i < FRAME_SIZE; i++) {
+        sig_e += signal[i] * signal[i];
+        sig_buf[i] = signal[i] * t->p.signal_gain;
+    }
+    biquad_in_place(t->p.sig_a, t->p.sig_b, sig_buf, t->signal_resp_mem, FRAME_SIZE);
+    biquad_in_place(t->p.noise_a, t->p.noise_b, noise_buf, t->noise_resp_mem, FRAME_SIZE);
+    for (int i = 0; i < FRAME_SIZE; i++) out_buf[i] = sig_buf[i] + noise_buf[i];
+    /* NoiseSimulator::vad, :380-397 */
+    if (sig_e > 1e9f) t->vad_count = 0;
+    else if (sig_e > 1e8f) t->vad_count -= 5;
+    else if (sig_e > 1e7f) t->vad_count += 1;
+    else t->vad_count += 2;
+    if (t->vad_count < 0) t->vad_count = 0;
+    if (t->vad_count > 15) t->vad_count = 15;
+    const float vad = t->vad_count >= 10 ? 0.0f : (t->vad_count > 0 ? 0.5f : 1.0f);
+    int cutoff = (vad == 0.0f && t->p.noise_gain == 0.0f) ? 0 : t->p.band_lp + 1;
+
+    /* main loop body, src/training.rs:126-159 */
+    shift_and_filter(t->clean, sig_buf);
+    shift_and_filter(t->noise, noise_buf);
+    shift_and_filter(t->comb, out_buf);
+    compute_frame_features(t->clean);
+    compute_frame_features(t->noise);
+    const int silence = compute_frame_features(t->comb);
+    if (silence) cutoff = 0;
+    float *gains = row + NB_FEATURES, *noise_level = row + NB_FEATURES + NB_BANDS;
+    for (int i = 0; i < NB_BANDS; i++) {
+        if (i < cutoff) {
+            const float ce = t->clean->ex[i], me = t->comb->ex[i];
+            gains[i] = (ce < 5e-2f && me < 5e-2f) ? -1.0f : fminf(sqrtf((ce + 1e-3f) / (me + 1e-3f)), 1.0f);
+        } else {
+            gains[i] = -1.0f;
+        }
+        noise_level[i] = log10f(t->noise->ex[i] + 1e-2f);
+    }
+    memcpy(row, t->comb->features, NB_FEATURES * sizeof(float));
+    row[NB_FEATURES + 2 * NB_BANDS] = vad;
+}

@@ -80,6 +80,27 @@ float nno_sigmoid(float x);
 double nno_run_batch(const nno_model *m, const float *in, float *out, float *vad, int32_t *pitch,
                      int n_streams, int n_frames, int n_threads, int *threads_used);
 
+
+/* ---- training-data rows: src/training.rs:113-161 (main loop) + :283-433 (NoiseSimulator) ---------------
+ * One "lane" = one NoiseSimulator + its three DenoiseFeatures (clean / noise / combined).  The file readers and
+ * the random draws of NoiseSimulator::randomize (src/training.rs:352-377, thread_rng: not reproducible) stay with
+ * the caller, which hands their RESULT in as nno_sim_params; everything arithmetic per frame is restated here. */
+#define NNO_TRAIN_ROW 87 /* 42 features + 22 gains + 22 noise levels + vad, src/training.rs:90,155-158 */
+typedef struct {
+    float signal_gain, noise_gain;         /* NoiseSimulator::{signal_gain, noise_gain}            */
+    float sig_a[2], sig_b[2];              /* sig_filter   (Biquad a, b; Default = zeros)          */
+    float noise_a[2], noise_b[2];          /* noise_filter                                         */
+    int32_t band_lp;                       /* NoiseSimulator::band_lp (new(): NB_BANDS - 1)        */
+} nno_sim_params;
+typedef struct nno_trainer nno_trainer;
+nno_trainer *nno_train_new(void);          /* NoiseSimulator::new + 3x DenoiseFeatures::new        */
+void nno_train_free(nno_trainer *t);
+void nno_train_set_params(nno_trainer *t, const nno_sim_params *p);
+/* one iteration of the main loop: signal/noise are the raw frames SignalReader::frame yields (i16-valued f32) */
+void nno_train_frame(nno_trainer *t, const float *signal480, const float *noise480, float *row87);
+/* EBAND_5MS.position(|x| x << 2 > lowpass).unwrap_or(NB_BANDS - 1), src/training.rs:373-376 */
+int32_t nno_train_band_lp(int32_t lowpass);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,7 +101,8 @@ int rnnoise_batch_process_device_pcm16(RNNoiseBatch *b, short *out, const short 
                                        long stream_stride, long frame_stride, void *cuda_stream);
 
 /* General layout: sample (s, t, i) at ptr[s*stream_stride + t*frame_stride + i*sample_stride] (element strides;
- * float samples, or int16 when pcm16 != 0).  Interleaved multi-channel audio, where every channel is its own stream
+ * pcm16 = 0: float samples in and out; 1: int16 in and out; 2: float in, int16 out (clamp + round); 3: int16 in,
+ * float out).  Interleaved multi-channel audio, where every channel is its own stream
  * (src/signal.rs:90-107, src/nnnoiseless.rs:301-330), is stream_stride = 1, sample_stride = n_channels,
  * frame_stride = 480 * n_channels. */
 int rnnoise_batch_process_device_strided(RNNoiseBatch *b, void *out, const void *in, int pcm16, float *vad, int n_frames,
@@ -159,6 +160,33 @@ int rnnoise_train_process_host(RNNoiseTrainer *t, float *rows, const float *sign
 int rnnoise_train_process_device(RNNoiseTrainer *t, float *rows, const float *signal, const float *noise, int n_frames,
                                  long stream_stride, long frame_stride, long row_lane_stride, long row_frame_stride,
                                  void *cuda_stream);
+
+/* ---- file front-end (additive; what the reference's `nnnoiseless` binary does around the path, src/nnnoiseless.rs) --
+ * decode (raw little-endian i16, or RIFF/WAVE: 8/16/24/32-bit integer and 32-bit float) -> resample to 48 kHz when
+ * the rate differs (dasp `Sinc<[f32; 16]>` at ratio rate/48000, on the GPU) -> one DenoiseState per channel ->
+ * the first frame's output is discarded, a trailing partial frame dropped -> clamp + round to i16 -> raw or 48 kHz
+ * 16-bit WAV.  All channels of all files of one call are streams of one batch. */
+typedef struct RNNoiseFileOptions {
+    int wav_in;            /* non-zero: inputs are WAV; 0: decided per file by a ".wav" extension (--wav-in)  */
+    int wav_out;           /* same for the outputs (--wav-out)                                                */
+    double sample_rate;    /* raw input only (--sample-rate); <= 0: 48000                                     */
+    int channels;          /* raw input only (--channels); <= 0: 1                                            */
+    const RNNModel *model; /* NULL: built-in (--model)                                                        */
+    int device;            /* CUDA device, -1: current                                                        */
+} RNNoiseFileOptions;
+int rnnoise_denoise_file(const char *in_path, const char *out_path, const RNNoiseFileOptions *opt);
+int rnnoise_denoise_files(int n_files, const char *const *in_paths, const char *const *out_paths,
+                          const RNNoiseFileOptions *opt);
+/* The decoders / encoders alone (host code).  wav: 1 = RIFF/WAVE, -1 = raw, 0 = by ".wav" extension.  Decoded samples are
+ * interleaved floats in the i16 range exactly as the binary feeds them to the path (src/nnnoiseless.rs:57-77, 190-228);
+ * *samples is malloc'ed: release with rnnoise_audio_free.  Writers: raw little-endian i16 or 48 kHz 16-bit WAV. */
+int rnnoise_audio_read(const char *path, int wav, int raw_channels, double raw_rate, float **samples, long *n_frames,
+                       int *channels, double *sample_rate);
+void rnnoise_audio_free(float *samples);
+int rnnoise_audio_write(const char *path, int wav, const short *pcm, long n_frames, int channels);
+/* The resampler alone, HOST buffers: in [n_in][channels] interleaved -> out [<= cap][channels]; returns the number of
+ * output sample frames (Resample::next_sample until the source runs dry, src/nnnoiseless.rs:104-131), < 0 on error. */
+long rnnoise_resample_host(float *out, long cap, const float *in, long n_in, int channels, double ratio, int device);
 
 /* Number of kernel launches issued by this library since load (bench evidence). */
 unsigned long long rnnoise_kernel_launches(void);

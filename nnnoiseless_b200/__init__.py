@@ -35,6 +35,8 @@ C_ABI_SYMBOLS = [
     "rnnoise_batch_get_taps", "rnnoise_batch_profile_step", "rnnoise_kernel_name",
     "rnnoise_train_create", "rnnoise_train_destroy", "rnnoise_train_lanes", "rnnoise_train_set_params",
     "rnnoise_train_band_lp", "rnnoise_train_process_host", "rnnoise_train_process_device",
+    "rnnoise_denoise_file", "rnnoise_denoise_files", "rnnoise_resample_host",
+    "rnnoise_audio_read", "rnnoise_audio_free", "rnnoise_audio_write",
     "rnnoise_kernel_launches", "rnnoise_last_error",
 ]
 
@@ -107,6 +109,18 @@ def lib():
     L.rnnoise_train_process_host.argtypes = [vp, vp, vp, vp, ci]
     L.rnnoise_train_process_device.restype = ci
     L.rnnoise_train_process_device.argtypes = [vp, vp, vp, vp, ci, C.c_long, C.c_long, C.c_long, C.c_long, vp]
+    L.rnnoise_denoise_file.restype = ci
+    L.rnnoise_denoise_file.argtypes = [C.c_char_p, C.c_char_p, vp]
+    L.rnnoise_denoise_files.restype = ci
+    L.rnnoise_denoise_files.argtypes = [ci, vp, vp, vp]
+    L.rnnoise_resample_host.restype = C.c_long
+    L.rnnoise_resample_host.argtypes = [vp, C.c_long, vp, C.c_long, ci, C.c_double, ci]
+    L.rnnoise_audio_read.restype = ci
+    L.rnnoise_audio_read.argtypes = [C.c_char_p, ci, ci, C.c_double, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_long),
+                                     C.POINTER(ci), C.POINTER(C.c_double)]
+    L.rnnoise_audio_free.argtypes = [C.POINTER(C.c_float)]
+    L.rnnoise_audio_write.restype = ci
+    L.rnnoise_audio_write.argtypes = [C.c_char_p, ci, vp, C.c_long, ci]
     L.rnnoise_kernel_name.restype = C.c_char_p
     L.rnnoise_kernel_name.argtypes = [ci]
     L.rnnoise_kernel_launches.restype = C.c_ulonglong

@@ -14,6 +14,9 @@ OBJ = os.path.join(HERE, "_obj")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libnnnoiseless_b200.so")
 WEIGHTS = os.path.join(HERE, "data", "weights.rnn")
+BINDIR = os.path.join(HERE, "bin")
+CLI = os.path.join(BINDIR, "nnnoiseless-b200")
+CLI_SRC = os.path.join(HERE, "..", "cli", "nnnoiseless_cli.cpp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -27,9 +30,10 @@ UNITS = [
     ("spectral.cu", []),
     ("rnn.cu", ["-DRNN_RT=256", "-DRNN_UNROLL=8"]),
     ("rnn_mma.cu", []),
+    ("frontend.cu", []),
     ("host.cu", []),
 ]
-HEADERS = ["common.cuh", "model.hpp", os.path.join("..", "..", "include", "rnnoise.h")]
+HEADERS = ["common.cuh", "model.hpp", "audio_io.hpp", os.path.join("..", "..", "include", "rnnoise.h")]
 
 
 def _newer(target, deps):
@@ -64,8 +68,19 @@ def build(force=False, verbose=False):
     if force or _newer(o, [s, WEIGHTS] + hdrs):
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", '-DNNB_WEIGHTS_PATH="%s"' % WEIGHTS, "-c", s, "-o", o]
         subprocess.run(cmd, check=True)
+    s = os.path.join(CSRC, "audio_io.cpp")
+    o = os.path.join(OBJ, "audio_io.cpp.o")
+    objs.append(o)
+    if force or _newer(o, [s] + hdrs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-c", s, "-o", o], check=True)
     if force or _newer(LIB, objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
+        subprocess.run(cmd, check=True)
+    # the command-line front-end (src/nnnoiseless.rs): a thin main() over rnnoise_denoise_files
+    os.makedirs(BINDIR, exist_ok=True)
+    if force or _newer(CLI, [CLI_SRC, LIB] + hdrs):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", CLI_SRC, "-o", CLI, "-L" + LIBDIR, "-lnnnoiseless_b200",
+               "-Wl,-rpath,$ORIGIN/../lib"]
         subprocess.run(cmd, check=True)
     with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
         f.write("".join(logs))

@@ -40,6 +40,16 @@ int fail(const std::string& what, cudaError_t e = cudaSuccess) {
     return -1;
 }
 
+}  // namespace
+
+// used by frontend.cu
+namespace nnb {
+int set_error(const std::string& what) { return fail(what); }
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+}  // namespace nnb
+
+namespace {
+
 #define CK(call)                                         \
     do {                                                 \
         cudaError_t e__ = (call);                        \
@@ -524,30 +534,31 @@ int ensure_stage(RNNoiseBatch* b, int n_frames, bool pcm) {
     return 0;
 }
 
-// in/out are float samples, or 16-bit PCM when pcm is set (element strides either way)
-int launch_stage(RNNoiseBatch* b, int i, const BatchBuffers& v, void* out, const void* in, bool pcm, float* vad, long stream_stride,
+// in/out are float samples or 16-bit PCM: fmt bit 0 = int16 input, bit 1 = int16 output (element strides either way)
+constexpr int kFmtF32 = 0, kFmtPcmIn = 1, kFmtPcmOut = 2, kFmtPcm = 3;
+int launch_stage(RNNoiseBatch* b, int i, const BatchBuffers& v, void* out, const void* in, int fmt, float* vad, long stream_stride,
                  long sample_stride, int slot, cudaStream_t s) {
     switch (i) {
-        case 0: CK(launch_hp_filter(v, in, pcm, stream_stride, sample_stride, slot, s)); break;
+        case 0: CK(launch_hp_filter(v, in, (fmt & kFmtPcmIn) != 0, stream_stride, sample_stride, slot, s)); break;
         case 1: CK(launch_pitch(v, slot, s)); break;
         case 2: CK(launch_analysis(v, b->d_tab, slot, s)); break;
         case 3:
             if (b->rnn_fp32) CK(launch_rnn(v, b->um.dm, b->d_tab, s));
             else CK(launch_rnn_mma(v, b->umm.dm, b->d_tab, s));
             break;
-        default: CK(launch_synthesis(v, b->d_tab, out, pcm, stream_stride, sample_stride, vad, s)); break;
+        default: CK(launch_synthesis(v, b->d_tab, out, (fmt & kFmtPcmOut) != 0, stream_stride, sample_stride, vad, s)); break;
     }
     return 0;
 }
 
 // One frame for all streams, serialised on ONE stream (profiling, NNB_SERIAL=1).  tev (optional): kNumKernels + 1 timing events.
-int step_serial(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad, long stream_stride, long sample_stride, cudaStream_t s,
+int step_serial(RNNoiseBatch* b, void* out, const void* in, int fmt, float* vad, long stream_stride, long sample_stride, cudaStream_t s,
                 cudaEvent_t* tev = nullptr) {
     const int slot = (int)(b->frame % HIST_SLOTS);
     const BatchBuffers v = view(b, b->frame);
     for (int i = 0; i < kNumKernels; i++) {
         if (tev) CK(cudaEventRecord(tev[i], s));
-        if (launch_stage(b, i, v, out, in, pcm, vad, stream_stride, sample_stride, slot, s)) return -1;
+        if (launch_stage(b, i, v, out, in, fmt, vad, stream_stride, sample_stride, slot, s)) return -1;
     }
     if (tev) CK(cudaEventRecord(tev[kNumKernels], s));
     g_launches.fetch_add(kNumKernels, std::memory_order_relaxed);
@@ -556,7 +567,7 @@ int step_serial(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad
 }
 
 // One frame for all streams on the five stage streams.  in_ready (optional): event the first stage must wait for.
-int step_pipelined(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad, long stream_stride, long sample_stride,
+int step_pipelined(RNNoiseBatch* b, void* out, const void* in, int fmt, float* vad, long stream_stride, long sample_stride,
                    cudaEvent_t in_ready) {
     const unsigned long long f = b->frame;
     const int slot = (int)(f % HIST_SLOTS), e = (int)(f % kEvRing);
@@ -565,7 +576,7 @@ int step_pipelined(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* 
     if (f >= (unsigned long long)PIPE_DEPTH) CK(cudaStreamWaitEvent(b->st[0], b->ev[kNumKernels - 1][(int)((f - PIPE_DEPTH) % kEvRing)], 0));
     for (int i = 0; i < kNumKernels; i++) {
         if (i > 0) CK(cudaStreamWaitEvent(b->st[i], b->ev[i - 1][e], 0));
-        if (launch_stage(b, i, v, out, in, pcm, vad, stream_stride, sample_stride, slot, b->st[i])) return -1;
+        if (launch_stage(b, i, v, out, in, fmt, vad, stream_stride, sample_stride, slot, b->st[i])) return -1;
         CK(cudaEventRecord(b->ev[i][e], b->st[i]));
     }
     g_launches.fetch_add(kNumKernels, std::memory_order_relaxed);
@@ -660,20 +671,22 @@ int rnnoise_batch_reset(RNNoiseBatch* b) {
     return zero_state(b);
 }
 
-static int process_device_impl(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad, int n_frames, long stream_stride,
+static int process_device_impl(RNNoiseBatch* b, void* out, const void* in, int fmt, float* vad, int n_frames, long stream_stride,
                                long sample_stride, long frame_stride, void* cuda_stream) {
     if (!b || !out || !in) return fail("null argument");
     if (sample_stride < 1) return fail("sample_stride must be >= 1");
     if (n_frames < 0) return fail("negative n_frames");
     if (n_frames == 0) return 0;
     CK(cudaSetDevice(b->device));
-    const size_t esz = pcm ? sizeof(short) : sizeof(float);
-    auto at = [&](const void* p, int t) { return (void*)((char*)p + (size_t)t * frame_stride * esz); };
+    if (fmt < 0 || fmt > 3) return fail("pcm16 must be 0..3");
+    const size_t esz_in = (fmt & kFmtPcmIn) ? sizeof(short) : sizeof(float), esz_out = (fmt & kFmtPcmOut) ? sizeof(short) : sizeof(float);
+    auto at_in = [&](const void* p, int t) { return (const void*)((const char*)p + (size_t)t * frame_stride * esz_in); };
+    auto at_out = [&](void* p, int t) { return (void*)((char*)p + (size_t)t * frame_stride * esz_out); };
     cudaStream_t us = (cudaStream_t)cuda_stream;
     if (b->serial) {
         cudaStream_t s = us ? us : b->st[0];
         for (int t = 0; t < n_frames; t++)
-            if (step_serial(b, at(out, t), at(in, t), pcm, vad ? vad + (size_t)t * b->n_streams : nullptr, stream_stride, sample_stride, s))
+            if (step_serial(b, at_out(out, t), at_in(in, t), fmt, vad ? vad + (size_t)t * b->n_streams : nullptr, stream_stride, sample_stride, s))
                 return -1;
         if (!us) CK(cudaStreamSynchronize(s));
         return 0;
@@ -684,7 +697,7 @@ static int process_device_impl(RNNoiseBatch* b, void* out, const void* in, bool 
         ready = b->ev_call;
     }
     for (int t = 0; t < n_frames; t++) {
-        if (step_pipelined(b, at(out, t), at(in, t), pcm, vad ? vad + (size_t)t * b->n_streams : nullptr, stream_stride, sample_stride,
+        if (step_pipelined(b, at_out(out, t), at_in(in, t), fmt, vad ? vad + (size_t)t * b->n_streams : nullptr, stream_stride, sample_stride,
                            t == 0 ? ready : nullptr))
             return -1;
     }
@@ -698,17 +711,19 @@ static int process_device_impl(RNNoiseBatch* b, void* out, const void* in, bool 
 
 int rnnoise_batch_process_device(RNNoiseBatch* b, float* out, const float* in, float* vad, int n_frames, long stream_stride,
                                  long frame_stride, void* cuda_stream) {
-    return process_device_impl(b, out, in, false, vad, n_frames, stream_stride, 1, frame_stride, cuda_stream);
+    return process_device_impl(b, out, in, kFmtF32, vad, n_frames, stream_stride, 1, frame_stride, cuda_stream);
 }
 
 int rnnoise_batch_process_device_pcm16(RNNoiseBatch* b, short* out, const short* in, float* vad, int n_frames, long stream_stride,
                                        long frame_stride, void* cuda_stream) {
-    return process_device_impl(b, out, in, true, vad, n_frames, stream_stride, 1, frame_stride, cuda_stream);
+    return process_device_impl(b, out, in, kFmtPcm, vad, n_frames, stream_stride, 1, frame_stride, cuda_stream);
 }
 
 int rnnoise_batch_process_device_strided(RNNoiseBatch* b, void* out, const void* in, int pcm16, float* vad, int n_frames, long stream_stride,
                                          long sample_stride, long frame_stride, void* cuda_stream) {
-    return process_device_impl(b, out, in, pcm16 != 0, vad, n_frames, stream_stride, sample_stride, frame_stride, cuda_stream);
+    if (pcm16 < 0 || pcm16 > 3) return fail("pcm16 must be 0..3");
+    static const int to_fmt[4] = {kFmtF32, kFmtPcm, kFmtPcmOut, kFmtPcmIn};
+    return process_device_impl(b, out, in, to_fmt[pcm16], vad, n_frames, stream_stride, sample_stride, frame_stride, cuda_stream);
 }
 
 const char* rnnoise_kernel_name(int i) { return (i >= 0 && i < kNumKernels) ? kKernelNames[i] : nullptr; }
@@ -722,7 +737,7 @@ int rnnoise_batch_profile_step(RNNoiseBatch* b, float* out, const float* in, flo
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->st[0];
     cudaEvent_t ev[kNumKernels + 1];
     for (int i = 0; i <= kNumKernels; i++) CK(cudaEventCreate(&ev[i]));
-    int rc = step_serial(b, out, in, false, vad, stream_stride, 1, st, ev);
+    int rc = step_serial(b, out, in, kFmtF32, vad, stream_stride, 1, st, ev);
     if (rc == 0) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail("profile_step sync", e);
@@ -756,10 +771,10 @@ static int process_host_impl(RNNoiseBatch* b, void* out, const void* in, bool pc
         CK(cudaEventRecord(b->ev_in[e], b->c_in));
         if (b->serial) {
             CK(cudaStreamWaitEvent(b->st[0], b->ev_in[e], 0));
-            if (step_serial(b, dout + t * fs * esz, din + t * fs * esz, pcm, b->stage_vad + (size_t)t * B, FRAME_SIZE, 1, b->st[0])) return -1;
+            if (step_serial(b, dout + t * fs * esz, din + t * fs * esz, pcm ? kFmtPcm : kFmtF32, b->stage_vad + (size_t)t * B, FRAME_SIZE, 1, b->st[0])) return -1;
             CK(cudaEventRecord(b->ev[kNumKernels - 1][e], b->st[0]));
         } else {
-            if (step_pipelined(b, dout + t * fs * esz, din + t * fs * esz, pcm, b->stage_vad + (size_t)t * B, FRAME_SIZE, 1, b->ev_in[e])) return -1;
+            if (step_pipelined(b, dout + t * fs * esz, din + t * fs * esz, pcm ? kFmtPcm : kFmtF32, b->stage_vad + (size_t)t * B, FRAME_SIZE, 1, b->ev_in[e])) return -1;
         }
         CK(cudaStreamWaitEvent(b->c_out, b->ev[kNumKernels - 1][e], 0));
         CK(cudaMemcpyAsync((char*)out + t * fs * esz, dout + t * fs * esz, fs * esz, cudaMemcpyDeviceToHost, b->c_out));

@@ -90,6 +90,10 @@ def lib():
         L.nno_run_batch.restype = C.c_double
         L.nno_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.nno_resample.restype = C.c_long
+        L.nno_resample.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_void_p, C.c_long]
+        L.nno_cli_frames.restype = C.c_long
+        L.nno_cli_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long]
         L.nno_train_new.restype = C.c_void_p
         L.nno_train_free.argtypes = [C.c_void_p]
         L.nno_train_set_params.argtypes = [C.c_void_p, C.c_void_p]
@@ -213,3 +217,62 @@ class Trainer:
 
 def train_band_lp(lowpass: int) -> int:
     return int(lib().nno_train_band_lp(int(lowpass)))
+
+
+def resample(x: np.ndarray, ratio: float) -> np.ndarray:
+    """Resample::next_sample (src/nnnoiseless.rs:104-131) until dry.  x: [n][channels] -> [k][channels]."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[:, None]
+    n, ch = x.shape
+    cap = int(n / ratio) + 16
+    out = np.empty((cap, ch), np.float32)
+    k = lib().nno_resample(_ptr(x), n, ch, float(ratio), _ptr(out), cap)
+    return out[:k]
+
+
+def cli_frames(model: Model, x48: np.ndarray) -> np.ndarray:
+    """main's frame loop (src/nnnoiseless.rs:301-330).  x48: [n][channels] float32 at 48 kHz -> int16 [m][channels]."""
+    x48 = np.ascontiguousarray(x48, dtype=np.float32)
+    if x48.ndim == 1:
+        x48 = x48[:, None]
+    n, ch = x48.shape
+    out = np.empty((max(n, 1), ch), np.int16)
+    m = lib().nno_cli_frames(model._h, _ptr(x48), n, ch, _ptr(out), out.shape[0])
+    return out[:m]
+
+
+def decode_wav(data: bytes):
+    """Independent (struct-based) restatement of what hound + wav_samples (src/nnnoiseless.rs:190-228) yield:
+    -> (samples [n][channels] float32, sample_rate).  Integer PCM 8/16/24/32-bit and 32-bit float."""
+    import struct
+    if data[:4] != b"RIFF":
+        raise ValueError("no RIFF tag found")
+    if data[8:12] != b"WAVE":
+        raise ValueError("no WAVE tag found")
+    p, fmt = 12, None
+    while p + 8 <= len(data):
+        cid, ln = data[p:p + 4], struct.unpack("<I", data[p + 4:p + 8])[0]
+        p += 8
+        if cid == b"fmt ":
+            tag, ch, rate, _, align, bits = struct.unpack("<HHIIHH", data[p:p + 16])
+            if tag == 0xFFFE:
+                tag = struct.unpack("<H", data[p + 24:p + 26])[0]
+            fmt = (tag, ch, rate, align // ch, bits)
+        elif cid == b"data":
+            tag, ch, rate, nbytes, bits = fmt
+            raw = np.frombuffer(data[p:p + ln], np.uint8)
+            n = ln // nbytes
+            if tag == 3:
+                v = raw[:n * 4].view("<f4").astype(np.float32) * np.float32(32767.0)
+            else:
+                b = raw[:n * nbytes].reshape(n, nbytes).astype(np.int64)
+                if nbytes == 1:
+                    s = b[:, 0] - 128
+                else:
+                    s = sum(b[:, i] << (8 * i) for i in range(nbytes))
+                    s = np.where(s >= 1 << (8 * nbytes - 1), s - (1 << (8 * nbytes)), s)
+                v = (s << (16 - bits) if bits < 16 else s >> (bits - 16)).astype(np.float32)
+            return v.reshape(-1, ch), float(rate)
+        p += ln + (ln & 1)
+    raise ValueError("no data chunk found")

@@ -1028,3 +1028,91 @@ void nno_train_frame(nno_trainer *t, const float *signal, const float *noise, fl
     memcpy(row, t->comb->features, NB_FEATURES * sizeof(float));
     row[NB_FEATURES + 2 * NB_BANDS] = vad;
 }
+
+/* ---- file front-end: src/nnnoiseless.rs --------------------------------------------------- */
+/* dasp_interpolate::sinc::Sinc<[f32; 16]> (0.11.0, restated): ring of 16 frames, idx saturating at depth. */
+typedef struct {
+    float ring[16]; /* logical order: ring[(first + i) % 16] = frames[i] */
+    int first;
+    int idx;
+} sinc16;
+
+static inline float sinc_at(const sinc16 *s, int i) { return s->ring[(s->first + i) % 16]; } /* Fixed::get wraps */
+
+/* Sinc::next_source_frame: Fixed::push overwrites the oldest frame, which becomes the newest */
+static void sinc_push(sinc16 *s, float x) {
+    s->ring[s->first] = x;
+    s->first = (s->first + 1) % 16;
+    if (s->idx < 8) s->idx += 1;
+}
+
+/* Sinc::interpolate */
+static float sinc_interpolate(const sinc16 *s, double x) {
+    const double pi = 3.14159265358979323846264338327950288;
+    const int depth = 8, len = 16;
+    const double phil = x, phir = 1.0 - x;
+    const int nl = s->idx, nr = s->idx + 1;
+    const int rightmost = nl + depth, leftmost = nr - depth;
+    int max_depth;
+    if (rightmost >= len) max_depth = len - depth;
+    else if (leftmost < 0) max_depth = depth + leftmost;
+    else max_depth = depth;
+    float v = 0.0f;
+    for (int n = 0; n < max_depth; n++) {
+        double a = pi * (phil + (double)n);
+        double first = (a == 0.0) ? 1.0 : sin(a) / a;
+        double second = 0.5 + 0.5 * cos(a / (double)depth);
+        v += (float)(first * second * (double)sinc_at(s, nl - n));
+        a = pi * (phir + (double)n);
+        first = (a == 0.0) ? 1.0 : sin(a) / a;
+        second = 0.5 + 0.5 * cos(a / (double)depth);
+        v += (float)(first * second * (double)sinc_at(s, nr + n));
+    }
+    return v;
+}
+
+long nno_resample(const float *in, long n_in, int channels, double ratio, float *out, long cap) {
+    sinc16 *st = (sinc16 *)calloc((size_t)channels, sizeof(sinc16));
+    double pos = 0.0;
+    long src = 0, k = 0;
+    for (;; k++) {
+        pos += ratio;
+        int dry = 0;
+        while (pos >= 1.0) {
+            pos -= 1.0;
+            if (src >= n_in) {
+                dry = 1;
+                break;
+            }
+            for (int c = 0; c < channels; c++) sinc_push(&st[c], in[src * channels + c]);
+            src++;
+        }
+        if (dry || k >= cap) break;
+        for (int c = 0; c < channels; c++) out[k * channels + c] = sinc_interpolate(&st[c], pos);
+    }
+    free(st);
+    return k;
+}
+
+long nno_cli_frames(const nno_model *m, const float *in, long n_in, int channels, int16_t *out, long cap) {
+    nno_state **st = (nno_state **)malloc(sizeof(nno_state *) * (size_t)channels);
+    for (int c = 0; c < channels; c++) st[c] = nno_state_new(m);
+    float ib[FRAME_SIZE], ob[FRAME_SIZE];
+    long written = 0;
+    for (long f = 0; (f + 1) * FRAME_SIZE <= n_in; f++) {
+        if (f > 0 && written + FRAME_SIZE > cap) break;
+        for (int c = 0; c < channels; c++) {
+            for (int i = 0; i < FRAME_SIZE; i++) ib[i] = in[(f * FRAME_SIZE + i) * channels + c];
+            nno_process_frame(st[c], ob, ib);
+            if (f == 0) continue; /* `first` frame is not written, src/nnnoiseless.rs:319-327 */
+            for (int i = 0; i < FRAME_SIZE; i++) {
+                float v = fminf(fmaxf(ob[i], -32768.0f), 32767.0f); /* :152-153, :167 */
+                out[(written + i) * channels + c] = (int16_t)roundf(v);
+            }
+        }
+        if (f > 0) written += FRAME_SIZE;
+    }
+    for (int c = 0; c < channels; c++) nno_state_free(st[c]);
+    free(st);
+    return written;
+}

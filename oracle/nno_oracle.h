@@ -101,6 +101,21 @@ void nno_train_frame(nno_trainer *t, const float *signal480, const float *noise4
 /* EBAND_5MS.position(|x| x << 2 > lowpass).unwrap_or(NB_BANDS - 1), src/training.rs:373-376 */
 int32_t nno_train_band_lp(int32_t lowpass);
 
+
+/* ---- file front-end: src/nnnoiseless.rs (the `nnnoiseless` binary) -------------------------------------
+ * The resampler is dasp_interpolate 0.11.0's `Sinc<[f32; 16]>` over dasp_ring_buffer 0.11.0's `Fixed`
+ * (Cargo.lock:292-300); both crates are NOT under /root/reference, so nno_resample restates their published
+ * algorithm (depth-8 Hann-windowed sinc, taps accumulated in f32 in the order left(n), right(n), n = 0..depth;
+ * ring indices wrap).  PARITY UNPINNED for the resampler: the reference holds no expected output for it
+ * (tests/cli.rs only checks exit status and the "no RIFF tag found" message). */
+/* Resample::next_sample (src/nnnoiseless.rs:104-131) until the source runs dry.  in: [n_in][channels] interleaved,
+ * out: [cap][channels]; returns the number of output sample frames (they never exceed cap). */
+long nno_resample(const float *in, long n_in, int channels, double ratio, float *out, long cap);
+/* main's frame loop (src/nnnoiseless.rs:301-330): per channel one DenoiseState, 480-sample frames, the first
+ * frame's output discarded, a trailing partial frame dropped, output clamped + rounded to i16 (:147-177).
+ * in: [n_in][channels] at 48 kHz; out: [cap][channels]; returns output sample frames written. */
+long nno_cli_frames(const nno_model *m, const float *in, long n_in, int channels, int16_t *out, long cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,4 +129,39 @@ class DenoiseBatch {
     ::RNNoiseBatch* b_;
 };
 
+/// Training-data rows (src/training.rs): n_lanes x (NoiseSimulator + 3 DenoiseFeatures) on one GPU; see rnnoise_train_*.
+class TrainingBatch {
+  public:
+    static constexpr int ROW = RNNOISE_TRAIN_ROW;  // 87 = 42 features + 22 gains + 22 noise levels + vad (src/training.rs:90)
+    explicit TrainingBatch(int n_lanes, int device = -1) : t_(rnnoise_train_create(n_lanes, device)) {
+        if (!t_) throw std::runtime_error(std::string("rnnoise_train_create: ") + rnnoise_last_error());
+    }
+    ~TrainingBatch() { rnnoise_train_destroy(t_); }
+    TrainingBatch(const TrainingBatch&) = delete;
+    TrainingBatch& operator=(const TrainingBatch&) = delete;
+    int lanes() const { return rnnoise_train_lanes(t_); }
+    /// the outcome of NoiseSimulator::randomize (src/training.rs:352-377) for lanes [first, first + n)
+    void set_params(int first_lane, int n, const RNNoiseSimParams* params) { check(rnnoise_train_set_params(t_, first_lane, n, params)); }
+    /// host buffers: signal, noise [n_frames][lanes][480] -> rows [n_frames][lanes][87]
+    void process_frames(float* rows, const float* signal, const float* noise, int n_frames) {
+        check(rnnoise_train_process_host(t_, rows, signal, noise, n_frames));
+    }
+
+  private:
+    static void check(int rc) {
+        if (rc != 0) throw std::runtime_error(rnnoise_last_error());
+    }
+    ::RNNoiseTrainer* t_;
+};
+
+/// The `nnnoiseless` binary's main() (src/nnnoiseless.rs:230-334) for a set of files denoised as one batch.
+inline void denoise_files(const std::vector<std::pair<std::string, std::string>>& in_out, const RNNoiseFileOptions* opt = nullptr) {
+    std::vector<const char*> ins, outs;
+    for (const auto& p : in_out) {
+        ins.push_back(p.first.c_str());
+        outs.push_back(p.second.c_str());
+    }
+    if (rnnoise_denoise_files((int)in_out.size(), ins.data(), outs.data(), opt) != 0) throw std::runtime_error(rnnoise_last_error());
+}
+
 }  // namespace nnnoiseless

@@ -102,3 +102,30 @@ def test_shard_streams_partition():
         assert spans[0][0] == 0 and sum(c for _, c in spans) == n
         for (s0, c0), (s1, _) in zip(spans, spans[1:]):
             assert s0 + c0 == s1
+
+
+def test_model_parser_fuzz_agrees_with_oracle(builtin_bytes):
+    """Loader hardening: on mutated / truncated / extended model images the product's parser and the
+    oracle's restatement of RnnModel::from_bytes (src/rnn.rs:116-232) accept exactly the same inputs, and an
+    accepted image round-trips byte for byte."""
+    from hypothesis import given, settings, strategies as st
+
+    good = builtin_bytes
+    # header bytes of the six layers (ni, nn, activation): the interesting places to corrupt
+    offs = [0, 1035, 4566, 24585, 85356, 87493]
+    hdr = [o + k for o in offs for k in range(3)]
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.tuples(st.sampled_from(hdr) | st.integers(0, len(good) - 1), st.integers(0, 255)), min_size=0, max_size=3),
+           st.integers(-40, 40))
+    def check(edits, dlen):
+        b = bytearray(good)
+        for pos, val in edits:
+            b[pos] = val
+        b = bytes(b[:len(b) + dlen]) if dlen < 0 else bytes(b) + bytes(dlen)
+        ours = nb.RnnModel.from_bytes(b)
+        assert (ours is not None) == oracle.model_accepts(b)
+        if ours is not None:
+            assert ours.to_bytes() == b
+
+    check()

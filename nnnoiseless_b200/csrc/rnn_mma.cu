@@ -73,81 +73,92 @@ __device__ __forceinline__ void store_pair(__half* Ahi, __half* Alo, int idx, fl
     *reinterpret_cast<__half2*>(Alo + idx) = __halves2half2(l0, l1);
 }
 
-// acc[i][mt][.] += A[:, phase columns] x W[:, tile tiles[i]]  for i < ntl, both 16-stream row tiles mt.
-template <int MAXT>
-__device__ __forceinline__ void run_tiles(const MmaPhase& ph, const __half* Ahi, const __half* Alo, int kp, int lane,
-                                          const int (&tiles)[MAXT], int ntl, float (&acc)[MAXT][2][4]) {
-    const int g = lane >> 2, t = lane & 3;
-    const uint2* wp[MAXT];  // this lane's slot in the fragments of tile i; one chunk further = + ntiles * 32
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t smem_addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_addr)
+                 : "memory");
+}
+
+// Output tiles of a warp: tile(i, gate) = gate * ot + warp + i * NWARP for i < cnt (gate 0 only, or z | r of a GRU).
+// acc[i * NGATE + gate][mt][.] += A[:, phase columns] x W[:, tile(i, gate)], both 16-stream row tiles mt.
+// One fragment pointer per GATE walks the chunks; the warp's other tiles sit at compile-time offsets from it.
+template <int NGATE, int MO>
+__device__ __forceinline__ void run_tiles(const MmaPhase& ph, const __half* Ahi, const __half* Alo, int kp, int lane, int warp, int ot,
+                                          int cnt, float (&acc)[NGATE * MO][2][4]) {
+    constexpr int TSTEP = NWARP * 32;  // fragments between a warp's consecutive tiles
+    const uint2* wg[NGATE];
 #pragma unroll
-    for (int i = 0; i < MAXT; i++) wp[i] = ph.wfrag + (size_t)(i < ntl ? tiles[i] : 0) * 32 + lane;
+    for (int gt = 0; gt < NGATE; gt++) wg[gt] = ph.wfrag + (size_t)(gt * ot + warp) * 32 + lane;
     const int wstep = ph.ntiles * 32;
-    uint2 bn[MAXT];
+    uint2 bn[NGATE * MO];
 #pragma unroll
-    for (int i = 0; i < MAXT; i++) bn[i] = (i < ntl) ? __ldg(wp[i]) : make_uint2(0u, 0u);
-    // row bases of this lane's A fragments: rows g and g + 8 of both row tiles, column 2t of the chunk
-    const int rb = g * kp + 2 * t;
-    const __half* ah0 = Ahi + rb;
-    const __half* al0 = Alo + rb;
-    const int r8 = 8 * kp, r16 = 16 * kp;
+    for (int i = 0; i < MO; i++)
+#pragma unroll
+        for (int gt = 0; gt < NGATE; gt++) bn[i * NGATE + gt] = (i < cnt) ? __ldg(wg[gt] + i * TSTEP) : make_uint2(0u, 0u);
+    // A fragments by ldmatrix: one x4 load = the 16x16 f16 tile in mma fragment order.  Lane l supplies the address of
+    // row (l & 7) + 8 ((l >> 3) & 1), column 8 (l >> 4) of the tile; rows are kp halves apart (kp = 8 mod 16: 16-byte
+    // aligned rows whose 8 addresses fall into 8 different 16-byte bank groups).
+    const int rb = ((lane & 7) + ((lane >> 3) & 1) * 8) * kp + (lane >> 4) * 8;
+    const uint32_t ah_base = (uint32_t)__cvta_generic_to_shared(Ahi + rb);
+    const uint32_t al_base = (uint32_t)__cvta_generic_to_shared(Alo + rb);
+    const uint32_t r16b = 32u * (uint32_t)kp;  // 16 rows further, in bytes
     const int nch = ph.nchunks;
     for (int kc = 0; kc < nch; kc++) {
-        uint2 b[MAXT];
+        uint2 b[NGATE * MO];
 #pragma unroll
-        for (int i = 0; i < MAXT; i++) b[i] = bn[i];
+        for (int i = 0; i < NGATE * MO; i++) b[i] = bn[i];
         if (kc + 1 < nch) {  // prefetch the next chunk's fragments while this chunk's MMAs run
 #pragma unroll
-            for (int i = 0; i < MAXT; i++) {
-                wp[i] += wstep;
-                if (i < ntl) bn[i] = __ldg(wp[i]);
-            }
+            for (int gt = 0; gt < NGATE; gt++) wg[gt] += wstep;
+#pragma unroll
+            for (int i = 0; i < MO; i++)
+#pragma unroll
+                for (int gt = 0; gt < NGATE; gt++)
+                    if (i < cnt) bn[i * NGATE + gt] = __ldg(wg[gt] + i * TSTEP);
         }
-        const int col = ph.col[kc];
+        const uint32_t cb = 2u * (uint32_t)ph.col[kc];
         uint32_t ah[2][4], al[2][4];
+        ldsm4(ah[0], ah_base + cb);
+        ldsm4(ah[1], ah_base + cb + r16b);
+        ldsm4(al[0], al_base + cb);
+        ldsm4(al[1], al_base + cb + r16b);
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-            const __half* ph_ = ah0 + col + mt * r16;
-            const __half* pl_ = al0 + col + mt * r16;
-            ah[mt][0] = *reinterpret_cast<const uint32_t*>(ph_);
-            ah[mt][1] = *reinterpret_cast<const uint32_t*>(ph_ + r8);
-            ah[mt][2] = *reinterpret_cast<const uint32_t*>(ph_ + 8);
-            ah[mt][3] = *reinterpret_cast<const uint32_t*>(ph_ + r8 + 8);
-            al[mt][0] = *reinterpret_cast<const uint32_t*>(pl_);
-            al[mt][1] = *reinterpret_cast<const uint32_t*>(pl_ + r8);
-            al[mt][2] = *reinterpret_cast<const uint32_t*>(pl_ + 8);
-            al[mt][3] = *reinterpret_cast<const uint32_t*>(pl_ + r8 + 8);
-        }
+        for (int i = 0; i < MO; i++) {
+            if (i < cnt) {
 #pragma unroll
-        for (int i = 0; i < MAXT; i++) {
-            if (i < ntl) {
+                for (int gt = 0; gt < NGATE; gt++)
 #pragma unroll
-                for (int mt = 0; mt < 2; mt++) {
-                    mma16816(acc[i][mt], ah[mt], b[i]);
-                    mma16816(acc[i][mt], al[mt], b[i]);
-                }
+                    for (int mt = 0; mt < 2; mt++) {
+                        mma16816(acc[i * NGATE + gt][mt], ah[mt], b[i * NGATE + gt]);
+                        mma16816(acc[i * NGATE + gt][mt], al[mt], b[i * NGATE + gt]);
+                    }
             }
         }
     }
 }
 
-template <int MAXT>
-__device__ __forceinline__ void init_bias(const MmaPhase& ph, int lane, const int (&tiles)[MAXT], int ntl, float (&acc)[MAXT][2][4]) {
+template <int NGATE, int MO>
+__device__ __forceinline__ void init_bias(const MmaPhase& ph, int lane, int warp, int ot, int cnt, float (&acc)[NGATE * MO][2][4]) {
     const int t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < MAXT; i++) {
-        float b0 = 0.0f, b1 = 0.0f;
-        if (i < ntl) {
-            b0 = __ldg(ph.bias + tiles[i] * 8 + 2 * t);
-            b1 = __ldg(ph.bias + tiles[i] * 8 + 2 * t + 1);
-        }
+    for (int i = 0; i < MO; i++)
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-            acc[i][mt][0] = b0;
-            acc[i][mt][1] = b1;
-            acc[i][mt][2] = b0;
-            acc[i][mt][3] = b1;
+        for (int gt = 0; gt < NGATE; gt++) {
+            float b0 = 0.0f, b1 = 0.0f;
+            if (i < cnt) {
+                const float2 bv = __ldg(reinterpret_cast<const float2*>(ph.bias + (gt * ot + warp + i * NWARP) * 8 + 2 * t));
+                b0 = bv.x;
+                b1 = bv.y;
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                acc[i * NGATE + gt][mt][0] = b0;
+                acc[i * NGATE + gt][mt][1] = b1;
+                acc[i * NGATE + gt][mt][2] = b0;
+                acc[i * NGATE + gt][mt][3] = b1;
+            }
         }
-    }
 }
 
 // One GRU layer for the block's 32 streams.  c_state: A columns of this layer's state; s_off: its offset in Hf.
@@ -164,15 +175,9 @@ __device__ void gru_layer(const MmaPhase& pzr, const MmaPhase& ph, int act, int 
     float zreg[MAXOT][2][4];
     {
         // z | r gates: tiles {z_j, r_j} for the owned output tiles j
-        int tiles[2 * MAXOT];
-#pragma unroll
-        for (int i = 0; i < MAXOT; i++) {
-            tiles[2 * i] = own[i];
-            tiles[2 * i + 1] = ot + own[i];
-        }
         float acc[2 * MAXOT][2][4];
-        init_bias<2 * MAXOT>(pzr, lane, tiles, 2 * cnt, acc);
-        run_tiles<2 * MAXOT>(pzr, Ahi, Alo, kp, lane, tiles, 2 * cnt, acc);
+        init_bias<2, MAXOT>(pzr, lane, warp, ot, cnt, acc);
+        run_tiles<2, MAXOT>(pzr, Ahi, Alo, kp, lane, warp, ot, cnt, acc);
 #pragma unroll
         for (int i = 0; i < MAXOT; i++) {
             if (i < cnt) {
@@ -197,12 +202,9 @@ __device__ void gru_layer(const MmaPhase& pzr, const MmaPhase& ph, int act, int 
     }
     __syncthreads();
     {
-        int tiles[MAXOT];
-#pragma unroll
-        for (int i = 0; i < MAXOT; i++) tiles[i] = own[i];
         float acc[MAXOT][2][4];
-        init_bias<MAXOT>(ph, lane, tiles, cnt, acc);
-        run_tiles<MAXOT>(ph, Ahi, Alo, kp, lane, tiles, cnt, acc);
+        init_bias<1, MAXOT>(ph, lane, warp, 0, cnt, acc);
+        run_tiles<1, MAXOT>(ph, Ahi, Alo, kp, lane, warp, 0, cnt, acc);
 #pragma unroll
         for (int i = 0; i < MAXOT; i++) {
             if (i < cnt) {
@@ -230,7 +232,7 @@ __device__ void gru_layer(const MmaPhase& pzr, const MmaPhase& ph, int act, int 
 }
 
 #ifndef RNN_MINB
-#define RNN_MINB 1
+#define RNN_MINB 2
 #endif
 __global__ void __launch_bounds__(NT, RNN_MINB) rnn_mma_kernel(BatchBuffers bb, DeviceModelMma m, const DeviceTables* __restrict__ tab) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -255,71 +257,55 @@ __global__ void __launch_bounds__(NT, RNN_MINB) rnn_mma_kernel(BatchBuffers bb, 
     }
     __syncthreads();
     {
-        // features [ns][42] and GRU state [ns][SS] of this block are contiguous in HBM: fetch them with 128-bit loads,
-        // all requests of a thread in flight before the first use (full blocks with 16-byte aligned bases)
+        // features [ns][42] and GRU state [ns][SS]: warp w takes rows w, w + NWARP, ...; lane l the columns l, l + 32, ...
+        // (coalesced row segments, no index divisions); every load of a thread is in flight before the first use.
+        constexpr int RPW = TS / NWARP;                 // rows per warp
+        constexpr int SK = (3 * MAX_NEURONS + 31) / 32;  // column slots per lane for the state (SS <= 3 * 128)
         const float* fsrc = bb.features + (size_t)s0 * NB_FEATURES;
         const float* ssrc = bb.gru_state + (size_t)s0 * SS;
-        const bool vec = ns == TS && ((reinterpret_cast<uintptr_t>(fsrc) | reinterpret_cast<uintptr_t>(ssrc)) & 15) == 0 && (SS & 3) == 0;
-        auto put_feat = [&](int e, float v) {
-            const int s = e / NB_FEATURES, j = e - s * NB_FEATURES;
-            __half hi, lo;
-            split_f16(v, hi, lo);
-            Ahi[s * kp + m.c_feat + j] = hi;
-            Alo[s * kp + m.c_feat + j] = lo;
-        };
-        auto put_state = [&](int e, float v) {
-            const int s = e / SS, j = e - s * SS;
-            int ac, ho;
-            if (j < m.nv) { ac = m.c_vad + j; ho = so_v + j; }
-            else if (j < m.nv + m.nn) { ac = m.c_noise + (j - m.nv); ho = so_n + (j - m.nv); }
-            else { ac = m.c_den + (j - m.nv - m.nn); ho = so_d + (j - m.nv - m.nn); }
-            Hf[s * hs + ho] = v;
-            __half hi, lo;
-            split_f16(v, hi, lo);
-            Ahi[s * kp + ac] = hi;
-            Alo[s * kp + ac] = lo;
-        };
-        if (vec) {
-            constexpr int NF4 = TS * NB_FEATURES / 4;          // 336
-            constexpr int FQ = (NF4 + NT - 1) / NT;            // 3 per thread
-            float4 fv[FQ];
+        const int nsk = (SS + 31) >> 5;
+        // A column / Hf column of state element j (the three GRU states are packed back to back in HBM)
+        int acol[SK], hcol[SK];
 #pragma unroll
-            for (int k = 0; k < FQ; k++) {
-                const int q = tid + k * NT;
-                fv[k] = q < NF4 ? __ldg(reinterpret_cast<const float4*>(fsrc) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const int ns4 = TS * SS / 4;
-            for (int q0 = 0; q0 < ns4; q0 += 8 * NT) {
-                float4 sv[8];
+        for (int k = 0; k < SK; k++) {
+            const int j = lane + 32 * k;
+            if (j < m.nv) { acol[k] = m.c_vad + j; hcol[k] = so_v + j; }
+            else if (j < m.nv + m.nn) { acol[k] = m.c_noise + (j - m.nv); hcol[k] = so_n + (j - m.nv); }
+            else { acol[k] = m.c_den + (j - m.nv - m.nn); hcol[k] = so_d + (j - m.nv - m.nn); }
+        }
+#pragma unroll 1
+        for (int r = 0; r < RPW; r++) {
+            const int row = warp + r * NWARP;
+            if (row >= ns) break;
+            float sv[SK], f0, f1 = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int q = q0 + tid + k * NT;
-                    sv[k] = q < ns4 ? __ldg(reinterpret_cast<const float4*>(ssrc) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int k = 0; k < SK; k++) sv[k] = (k < nsk && lane + 32 * k < SS) ? __ldg(ssrc + (size_t)row * SS + lane + 32 * k) : 0.0f;
+            f0 = __ldg(fsrc + row * NB_FEATURES + lane);
+            if (lane + 32 < NB_FEATURES) f1 = __ldg(fsrc + row * NB_FEATURES + lane + 32);
+            __half* ahr = Ahi + row * kp;
+            __half* alr = Alo + row * kp;
+            float* hfr = Hf + row * hs;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int q = q0 + tid + k * NT;
-                    if (q < ns4) {
-                        put_state(4 * q, sv[k].x);
-                        put_state(4 * q + 1, sv[k].y);
-                        put_state(4 * q + 2, sv[k].z);
-                        put_state(4 * q + 3, sv[k].w);
-                    }
+            for (int k = 0; k < SK; k++) {
+                if (k < nsk && lane + 32 * k < SS) {
+                    hfr[hcol[k]] = sv[k];
+                    __half hi, lo;
+                    split_f16(sv[k], hi, lo);
+                    ahr[acol[k]] = hi;
+                    alr[acol[k]] = lo;
                 }
             }
-#pragma unroll
-            for (int k = 0; k < FQ; k++) {
-                const int q = tid + k * NT;
-                if (q < NF4) {
-                    put_feat(4 * q, fv[k].x);
-                    put_feat(4 * q + 1, fv[k].y);
-                    put_feat(4 * q + 2, fv[k].z);
-                    put_feat(4 * q + 3, fv[k].w);
+            {
+                __half hi, lo;
+                split_f16(f0, hi, lo);
+                ahr[m.c_feat + lane] = hi;
+                alr[m.c_feat + lane] = lo;
+                if (lane + 32 < NB_FEATURES) {
+                    split_f16(f1, hi, lo);
+                    ahr[m.c_feat + lane + 32] = hi;
+                    alr[m.c_feat + lane + 32] = lo;
                 }
             }
-        } else {
-            for (int i = tid; i < ns * NB_FEATURES; i += NT) put_feat(i, fsrc[i]);
-            for (int i = tid; i < ns * SS; i += NT) put_state(i, ssrc[i]);
         }
     }
     __syncthreads();
@@ -334,8 +320,8 @@ __global__ void __launch_bounds__(NT, RNN_MINB) rnn_mma_kernel(BatchBuffers bb, 
             if (tiles[i] < ntile) cnt = i + 1;
         }
         float acc[MAXOT][2][4];
-        init_bias<MAXOT>(m.dense, lane, tiles, cnt, acc);
-        run_tiles<MAXOT>(m.dense, Ahi, Alo, kp, lane, tiles, cnt, acc);
+        init_bias<1, MAXOT>(m.dense, lane, warp, 0, cnt, acc);
+        run_tiles<1, MAXOT>(m.dense, Ahi, Alo, kp, lane, warp, 0, cnt, acc);
 #pragma unroll
         for (int i = 0; i < MAXOT; i++)
             if (i < cnt)
@@ -358,10 +344,9 @@ __global__ void __launch_bounds__(NT, RNN_MINB) rnn_mma_kernel(BatchBuffers bb, 
 
     // ---- vad_output (src/rnn.rs:359): one neuron -> tile 0, warp 0 (no barrier needed: it only reads the vad state) ----
     if (warp == 0) {
-        int tiles[1] = {0};
         float acc[1][2][4];
-        init_bias<1>(m.vad_out, lane, tiles, 1, acc);
-        run_tiles<1>(m.vad_out, Ahi, Alo, kp, lane, tiles, 1, acc);
+        init_bias<1, 1>(m.vad_out, lane, 0, 0, 1, acc);
+        run_tiles<1, 1>(m.vad_out, Ahi, Alo, kp, lane, 0, 0, 1, acc);
         if (t == 0) {
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
@@ -380,11 +365,10 @@ __global__ void __launch_bounds__(NT, RNN_MINB) rnn_mma_kernel(BatchBuffers bb, 
 
     // ---- denoise_output (src/rnn.rs:378): 22 band gains ----
     {
-        int tiles[1] = {warp};
         if (warp < (NB_BANDS + 7) / 8) {
             float acc[1][2][4];
-            init_bias<1>(m.out, lane, tiles, 1, acc);
-            run_tiles<1>(m.out, Ahi, Alo, kp, lane, tiles, 1, acc);
+            init_bias<1, 1>(m.out, lane, warp, 0, 1, acc);
+            run_tiles<1, 1>(m.out, Ahi, Alo, kp, lane, warp, 0, 1, acc);
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
 #pragma unroll
@@ -403,14 +387,16 @@ __global__ void __launch_bounds__(NT, RNN_MINB) rnn_mma_kernel(BatchBuffers bb, 
         }
     }
     // ---- state write-back; silent frames leave the RNN state untouched (src/denoise.rs:102) ----
-    for (int i = tid; i < TS * SS; i += NT) {
-        const int s = i / SS, j = i - s * SS;
-        if (s < ns && !bb.silence[s0 + s]) {
+    for (int row = warp; row < ns; row += NWARP) {
+        if (bb.silence[s0 + row]) continue;
+        float* dst = bb.gru_state + (size_t)(s0 + row) * SS;
+        const float* hfr = Hf + row * hs;
+        for (int j = lane; j < SS; j += 32) {
             int ho;
             if (j < m.nv) ho = so_v + j;
             else if (j < m.nv + m.nn) ho = so_n + (j - m.nv);
             else ho = so_d + (j - m.nv - m.nn);
-            bb.gru_state[(size_t)(s0 + s) * SS + j] = Hf[s * hs + ho];
+            dst[j] = hfr[ho];
         }
     }
 }

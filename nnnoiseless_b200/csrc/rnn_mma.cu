@@ -28,20 +28,19 @@ constexpr int NT = NWARP * 32;
 constexpr int MAXOT = 16 / NWARP;  // output tiles (8 neurons) per warp: NWARP * MAXOT tiles cover layers up to 128 neurons
 constexpr float WEIGHTS_SCALE = 1.0f / 256.0f;
 
+// src/util.rs:3-27, branch-free (the lanes of a warp hold different neurons): same arithmetic on |x| clamped to 8, the
+// saturations (NaN -> 1 like the reference's `!(x < 8)`) applied as selects at the end.
 __device__ __forceinline__ float tansig_approx(float x, const float* __restrict__ table) {
-    if (!(x < 8.0f)) return 1.0f;
-    if (!(x > -8.0f)) return -1.0f;
-    float sign = 1.0f;
-    if (x < 0.0f) {
-        x = -x;
-        sign = -1.0f;
-    }
-    float fi = floorf(0.5f + 25.0f * x);
-    x -= 0.04f * fi;
+    const float sign = (x < 0.0f) ? -1.0f : 1.0f;
+    float ax = fminf(fabsf(x), 8.0f);  // fminf(NaN, 8) = 8: the table index stays in range
+    const float fi = floorf(0.5f + 25.0f * ax);
+    ax -= 0.04f * fi;
     float y = table[(int)fi];
-    float dy = 1.0f - y * y;
-    y = y + x * dy * (1.0f - y * x);
-    return sign * y;
+    const float dy = 1.0f - y * y;
+    y = y + ax * dy * (1.0f - y * ax);
+    y = sign * y;
+    y = !(x > -8.0f) ? -1.0f : y;
+    return !(x < 8.0f) ? 1.0f : y;
 }
 __device__ __forceinline__ float sigmoid_approx(float x, const float* __restrict__ table) {
     return 0.5f + 0.5f * tansig_approx(0.5f * x, table);
@@ -104,19 +103,7 @@ __device__ __forceinline__ void run_tiles(const MmaPhase& ph, const __half* Ahi,
     const uint32_t al_base = (uint32_t)__cvta_generic_to_shared(Alo + rb);
     const uint32_t r16b = 32u * (uint32_t)kp;  // 16 rows further, in bytes
     const int nch = ph.nchunks;
-    for (int kc = 0; kc < nch; kc++) {
-        uint2 b[NGATE * MO];
-#pragma unroll
-        for (int i = 0; i < NGATE * MO; i++) b[i] = bn[i];
-        if (kc + 1 < nch) {  // prefetch the next chunk's fragments while this chunk's MMAs run
-#pragma unroll
-            for (int gt = 0; gt < NGATE; gt++) wg[gt] += wstep;
-#pragma unroll
-            for (int i = 0; i < MO; i++)
-#pragma unroll
-                for (int gt = 0; gt < NGATE; gt++)
-                    if (i < cnt) bn[i * NGATE + gt] = __ldg(wg[gt] + i * TSTEP);
-        }
+    auto chunk = [&](int kc, const uint2 (&b)[NGATE * MO]) {
         const uint32_t cb = 2u * (uint32_t)ph.col[kc];
         uint32_t ah[2][4], al[2][4];
         ldsm4(ah[0], ah_base + cb);
@@ -135,7 +122,30 @@ __device__ __forceinline__ void run_tiles(const MmaPhase& ph, const __half* Ahi,
                     }
             }
         }
+    };
+    auto fetch = [&](uint2 (&dst)[NGATE * MO]) {  // fragments of the next chunk
+#pragma unroll
+        for (int gt = 0; gt < NGATE; gt++) wg[gt] += wstep;
+#pragma unroll
+        for (int i = 0; i < MO; i++)
+#pragma unroll
+            for (int gt = 0; gt < NGATE; gt++)
+                if (i < cnt) dst[i * NGATE + gt] = __ldg(wg[gt] + i * TSTEP);
+    };
+    // two fragment buffers used alternately (chunk loop unrolled by two): the next chunk's fragments are in flight
+    // while this chunk's MMAs run, and no register copies are needed between iterations
+    uint2 bm[NGATE * MO];
+#pragma unroll
+    for (int i = 0; i < NGATE * MO; i++) bm[i] = make_uint2(0u, 0u);
+    int kc = 0;
+#pragma unroll 1
+    for (; kc + 1 < nch; kc += 2) {
+        fetch(bm);
+        chunk(kc, bn);
+        if (kc + 2 < nch) fetch(bn);
+        chunk(kc + 1, bm);
     }
+    if (kc < nch) chunk(kc, bn);
 }
 
 template <int NGATE, int MO>
@@ -162,7 +172,12 @@ __device__ __forceinline__ void init_bias(const MmaPhase& ph, int lane, int warp
 }
 
 // One GRU layer for the block's 32 streams.  c_state: A columns of this layer's state; s_off: its offset in Hf.
-__device__ void gru_layer(const MmaPhase& pzr, const MmaPhase& ph, int act, int nn, int c_state, int c_rh, int s_off,
+#ifdef RNN_NOINLINE
+#define RNN_GRU_ATTR __noinline__
+#else
+#define RNN_GRU_ATTR
+#endif
+__device__ RNN_GRU_ATTR void gru_layer(const MmaPhase& pzr, const MmaPhase& ph, int act, int nn, int c_state, int c_rh, int s_off,
                           __half* Ahi, __half* Alo, int kp, float* Hf, int hs, const float* table) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int ot = (nn + 7) >> 3;  // output tiles of this layer

@@ -75,7 +75,6 @@ constexpr int SMEM_FLOATS = OFF_TASK + SB * 29;
 static_assert(SB * YN2_LD <= SB * Y4_LD && SB * YY_LD <= SB * Y4_LD, "yn2 / yy must fit in the Y4 region");
 static_assert(SMEM_FLOATS * 4 + 1024 <= 227 * 1024, "tile must fit in one SM");
 
-__constant__ int c_second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};  // src/pitch.rs:489
 
 __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
     return __fdiv_rn(xy, __fsqrt_rn(fa(1.0f, fm(xx, yy))));  // src/pitch.rs:485-487
@@ -527,11 +526,11 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         SI[2 * SB + ls] = t0;
         // Compact list of the inner products remove_doubling will need (src/pitch.rs:134,152-168): xy(t0), then
         // for k = 2.. while t1 >= min_period: lags t1 and t1b.  Entry = stream << 16 | q << 10 | lag.
+        // (k is a compile-time constant in the unrolled loops below: the divisions by 2k become multiply-shifts)
         int nk = 0;
-        for (int k = 2; k <= 15; k++) {
-            if ((2 * t0 + k) / (2 * k) < MIN_PERIOD2) break;
-            nk++;
-        }
+#pragma unroll
+        for (int k = 2; k <= 15; k++)
+            if (nk == k - 2 && (2 * t0 + k) / (2 * k) >= MIN_PERIOD2) nk++;
         const int n = (lane < SB) ? 1 + 2 * nk : 0;
         int incl = n;
 #pragma unroll
@@ -543,12 +542,16 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         if (lane < SB) {
             int* tk = TASK + (incl - n);
             tk[0] = (lane << 16) | (1 << 10) | t0;
-            for (int j = 0; j < nk; j++) {
-                const int k = 2 + j;
-                const int t1 = (2 * t0 + k) / (2 * k);
-                const int t1b = (k == 2) ? ((t1 + t0 > HALF_MAX) ? t0 : t0 + t1) : (2 * c_second_check[k] * t0 + k) / (2 * k);
-                tk[1 + 2 * j] = (lane << 16) | ((2 + 2 * j) << 10) | t1;
-                tk[2 + 2 * j] = (lane << 16) | ((3 + 2 * j) << 10) | t1b;
+#pragma unroll
+            for (int k = 2; k <= 15; k++) {
+                constexpr int sc[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};  // SECOND_CHECK, src/pitch.rs:489
+                const int j = k - 2;
+                if (j < nk) {
+                    const int t1 = (2 * t0 + k) / (2 * k);
+                    const int t1b = (k == 2) ? ((t1 + t0 > HALF_MAX) ? t0 : t0 + t1) : (2 * sc[k] * t0 + k) / (2 * k);
+                    tk[1 + 2 * j] = (lane << 16) | ((2 + 2 * j) << 10) | t1;
+                    tk[2 + 2 * j] = (lane << 16) | ((3 + 2 * j) << 10) | t1b;
+                }
             }
         }
     }
@@ -614,12 +617,14 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         const float g0 = pitch_gain(xy, xx, yyv);
         float g = g0;
         int t = t0;
+#pragma unroll
         for (int k = 2; k <= 15; k++) {
+            constexpr int sc[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};  // SECOND_CHECK, src/pitch.rs:489
             const int t1 = (2 * t0 + k) / (2 * k);
             if (t1 < MIN_PERIOD2) break;
             int t1b;
             if (k == 2) t1b = (t1 + t0 > HALF_MAX) ? t0 : t0 + t1;
-            else t1b = (2 * c_second_check[k] * t0 + k) / (2 * k);
+            else t1b = (2 * sc[k] * t0 + k) / (2 * k);
             xy = fm(fa(ipr[2 + 2 * (k - 2)], ipr[3 + 2 * (k - 2)]), 0.5f);
             yyv = fm(fa(yy[t1], yy[t1b]), 0.5f);
             const float g1 = pitch_gain(xy, xx, yyv);

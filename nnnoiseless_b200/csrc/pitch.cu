@@ -39,7 +39,7 @@ __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); 
 constexpr int SB = PITCH_SB;    // streams per block (lane-per-stream phases use lanes 0..SB-1, mirrored on the others)
 constexpr int NT = PITCH_NT;    // threads per block
 constexpr int NW = NT / 32;
-constexpr int BLOCKS_PER_SM = (227 * 1024) / ((SB * (868 + 436 + 2 * 149 + 31 + 11 + 29) + 64 * SB + 64) * 4 + 1024);
+constexpr int BLOCKS_PER_SM = (227 * 1024) / ((SB * (868 + 436 + 2 * 149 + 31 + 11 + 29 + 39) + 64 * SB + 64) * 4 + 1024);
 static_assert(SB <= 32 && (32 % SB) == 0 && NW >= 4, "phase-to-warp assignment below assumes >= 4 warps");
 constexpr int PB = PITCH_BUF_SIZE / 2;                                 // 864
 constexpr int MAXP = PITCH_MAX_PERIOD - 3 * PITCH_MIN_PERIOD;          // 588
@@ -71,7 +71,12 @@ constexpr int OFF_IPR = OFF_PG + SB;             // [SB][31]
 constexpr int OFF_FX = OFF_IPR + SB * IPR_LD;    // [SB][11]
 constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [4][SB]: best4, second4, t0, t; then 4 counters
 constexpr int OFF_TASK = OFF_SI + 4 * SB + 4;    // int [SB*29]: compacted remove_doubling inner-product tasks
-constexpr int SMEM_FLOATS = OFF_TASK + SB * 29;
+constexpr int CK_STEP = 8;                         // fine running energy: one checkpoint every 8 lags
+constexpr int CK_N = (NL2 + CK_STEP - 1) / CK_STEP;  // 37
+constexpr int CK_LD = 39;
+constexpr int OFF_CK = OFF_TASK + SB * 29;          // [SB][39]
+constexpr int SMEM_FLOATS = OFF_CK + SB * CK_LD;
+static_assert(CK_N <= CK_LD, "checkpoint row too short");
 static_assert(SB * YN2_LD <= SB * Y4_LD && SB * YY_LD <= SB * Y4_LD, "yn2 / yy must fit in the Y4 region");
 static_assert(SMEM_FLOATS * 4 + 1024 <= 227 * 1024, "tile must fit in one SM");
 
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
     int* SI = reinterpret_cast<int*>(sm + OFF_SI);
     int* CTR = SI + 4 * SB;  // [0] xcorr task counter, [1] rd task counter, [2] number of rd tasks
     int* TASK = reinterpret_cast<int*>(sm + OFF_TASK);
+    float* CK = sm + OFF_CK;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ls = lane % SB;  // lane-per-stream phases: lanes >= SB mirror lanes < SB (same reads, same writes)
@@ -375,6 +381,31 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
                 if (4 * m + d + 1 < XC_LD) out[4 * m + d + 1] = y;
             }
         }
+    } else if (warp == NW - 3) {
+        // y_sq_norm of find_best_pitch(xcorr, y, 480) (the FINE search, src/pitch.rs:97): a 774-step chain that needs
+        // nothing but the whitened buffer, so it runs here, under the coarse cross-correlation, instead of after it.
+        // Only every 8th value is kept (CK[m] = value seen at fine lag 8 m); Ph8 replays the few steps it needs from
+        // the nearest checkpoint -- same operations in the same order, hence the same values.
+        const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
+        float y = 1.0f;
+#pragma unroll 4
+        for (int m = 0; m < HALF_N / 4; m++) {
+            const float4 v = row[m];
+            y = fa(y, fm(v.x, v.x));
+            y = fa(y, fm(v.y, v.y));
+            y = fa(y, fm(v.z, v.z));
+            y = fa(y, fm(v.w, v.w));
+        }
+        float* ck = CK + ls * CK_LD;
+        ck[0] = y;
+#pragma unroll 2
+        for (int m = 0; m < (CK_N - 1) * CK_STEP / 4; m++) {
+            const float4 va = row[HALF_N / 4 + m], vb = row[m];
+            const float a[4] = {va.x, va.y, va.z, va.w}, b[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int d = 0; d < 4; d++) y = fmaxf(fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d]))), 1.0f);
+            if ((m & 1) == 1) ck[(m + 1) >> 1] = y;  // after 4 (m + 1) steps
+        }
     } else if (warp == NW - 1) {
         // xx = inner_prod(x, x, 480) with its four interleaved accumulators (src/pitch.rs:133, 225-244)
         const float4* xr = reinterpret_cast<const float4*>(P + ls * P_LD + HALF_MAX);
@@ -428,9 +459,7 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
     __syncthreads();
     PPROF(4);
 
-    // ---- Ph6a: warp 0: coarse best/second (serial over lags, lane = stream; src/pitch.rs:83-84).
-    // warp 1: fine running energy.  The 4x-decimated copy is dead: YN2 reuses it. ----
-    float* YN2 = Y4;
+    // ---- Ph6a: warp 0: coarse best/second (serial over lags, lane = stream; src/pitch.rs:83-84) ----
     if (warp == 0) {
         BestTwo b2;
         const float* xc = XC + ls * XC_LD;
@@ -439,30 +468,6 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         for (int i = 0; i < NL4; i++) b2.consider(i, xc[i], yn[i]);
         SI[0 * SB + ls] = b2.best;
         SI[1 * SB + ls] = b2.second;
-    } else if (warp == 1) {
-        // y_sq_norm of find_best_pitch(xcorr, y, 480): YN2[i] = value seen at fine lag i
-        const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
-        float y = 1.0f;
-#pragma unroll 4
-        for (int m = 0; m < HALF_N / 4; m++) {
-            const float4 v = row[m];
-            y = fa(y, fm(v.x, v.x));
-            y = fa(y, fm(v.y, v.y));
-            y = fa(y, fm(v.z, v.z));
-            y = fa(y, fm(v.w, v.w));
-        }
-        float* out = YN2 + ls * YN2_LD;
-        out[0] = y;
-#pragma unroll 2
-        for (int m = 0; m < (NL2 + 3) / 4; m++) {
-            const float4 va = row[HALF_N / 4 + m], vb = row[m];
-            const float a[4] = {va.x, va.y, va.z, va.w}, b[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                y = fmaxf(fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d]))), 1.0f);
-                if (4 * m + d + 1 < YN2_LD) out[4 * m + d + 1] = y;
-            }
-        }
     }
     __syncthreads();
     PPROF(5);
@@ -497,7 +502,25 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
     if (warp == 0) {
         const int best4 = SI[0 * SB + ls], second4 = SI[1 * SB + ls];
         const float* fx = FX + ls * FX_LD;
-        const float* yn = YN2 + ls * YN2_LD;
+        // fine running energy at lag i, replayed from the nearest checkpoint at or below it (lags are asked in
+        // ascending order): step i -> i + 1 is y = max(y + p[480 + i]^2 - p[i]^2, 1)  (src/pitch.rs:401-402)
+        const float* prow8 = P + ls * P_LD;
+        const float* ck = CK + ls * CK_LD;
+        int ycur = -1;
+        float yval = 0.0f;
+        auto yn_at = [&](int i) -> float {
+            const int c = i & ~(CK_STEP - 1);
+            if (ycur < c) {
+                ycur = c;
+                yval = ck[c / CK_STEP];
+            }
+            while (ycur < i) {
+                const float a = prow8[HALF_N + ycur], b = prow8[ycur];
+                yval = fmaxf(fa(yval, fs(fm(a, a), fm(b, b))), 1.0f);
+                ycur++;
+            }
+            return yval;
+        };
         const int cA = 2 * best4, cB = 2 * second4;
         const int baseA = min(max(cA - 2, 0), NL2 - 5), baseB = min(max(cB - 2, 0), NL2 - 5);
         // xcorr at fine lag i: computed iff |i - 2 best| <= 2 or |i - 2 second| <= 2 (src/pitch.rs:90-95), else 0
@@ -512,8 +535,8 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         const int c0 = min(cA, cB) - 2, c1 = max(cA, cB) - 2;
         const int lo0 = max(c0, 0), hi0 = min(c0 + 4, NL2 - 1);
         const int lo1 = max(max(c1, 0), hi0 + 1), hi1 = min(c1 + 4, NL2 - 1);
-        for (int i = lo0; i <= hi0; i++) b2.consider(i, xcf(i), yn[i]);
-        for (int i = lo1; i <= hi1; i++) b2.consider(i, xcf(i), yn[i]);
+        for (int i = lo0; i <= hi0; i++) b2.consider(i, xcf(i), yn_at(i));
+        for (int i = lo1; i <= hi1; i++) b2.consider(i, xcf(i), yn_at(i));
         const int best = b2.best;
         int offset = 0;
         if (best > 0 && best < NL2 - 1) {
@@ -559,7 +582,7 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
     PPROF(7);
 
     // ---- Ph9: yy_lookup chain (warp NW-1 first) + remove_doubling inner products on all warps ----
-    float* YY = Y4;  // yn2 is dead from here on
+    float* YY = Y4;  // the 4x-decimated copy is dead from here on
     if (warp == NW - 1) {
         // yy_lookup (src/pitch.rs:135-142): stored clamped at 0, carried unclamped; i = 1..384 walks the rows downwards
         const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);

@@ -10,7 +10,7 @@ namespace nnb {
 
 constexpr int ST = 128;  // threads per block (one block per stream)
 
-// ---- 480-point complex Stockham FFT (forward, e^{-i}), radices 4,4,5,3,2 ---------------------------
+// ---- 480-point complex Stockham FFT (forward, e^{-i}), radices 4,4,5,6 ---------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -35,6 +35,20 @@ __device__ __forceinline__ void butterfly(float2* a) {
         a[0] = cadd(a[0], t1);
         a[1] = make_float2(m1.x + s * d.y, m1.y - s * d.x);
         a[2] = make_float2(m1.x - s * d.y, m1.y + s * d.x);
+    } else if (R == 6) {
+        // 6 = 2 x 3: E = DFT3(a0, a2, a4), O = DFT3(a1, a3, a5);  X[k] = E[k] + W6^k O[k],  X[k + 3] = E[k] - W6^k O[k]
+        const float h = 0.5f, s = 0.86602540378443864676f;
+        float2 e[3] = {a[0], a[2], a[4]}, o[3] = {a[1], a[3], a[5]};
+        butterfly<3>(e);
+        butterfly<3>(o);
+        const float2 t1 = make_float2(h * o[1].x + s * o[1].y, h * o[1].y - s * o[1].x);    // o1 * (1/2, -s)
+        const float2 t2 = make_float2(s * o[2].y - h * o[2].x, -h * o[2].y - s * o[2].x);   // o2 * (-1/2, -s)
+        a[0] = cadd(e[0], o[0]);
+        a[3] = csub(e[0], o[0]);
+        a[1] = cadd(e[1], t1);
+        a[4] = csub(e[1], t1);
+        a[2] = cadd(e[2], t2);
+        a[5] = csub(e[2], t2);
     } else if (R == 5) {
         const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
         const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
@@ -73,13 +87,14 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ x, floa
     __syncthreads();
 }
 
-// forward FFT of a[480]; result lands in b.  Both buffers in shared memory; tw = tw480 table.
+// forward FFT of a[480]; FOUR passes, so the result lands back in a (b is the pong buffer).  Both buffers in shared
+// memory; tw = tw480 table.  (The last two radices 3 and 2 are one radix-6 pass: one barrier and one trip through
+// shared memory less.)
 __device__ void fft480(float2* a, float2* b, const float2* tw) {
     stockham_pass<4, 480, 1>(a, b, tw);
     stockham_pass<4, 120, 4>(b, a, tw);
     stockham_pass<5, 30, 16>(a, b, tw);
-    stockham_pass<3, 6, 80>(b, a, tw);
-    stockham_pass<2, 2, 240>(a, b, tw);
+    stockham_pass<6, 6, 80>(b, a, tw);
 }
 
 // Two independent 480-point FFTs advanced together (same indices, same twiddles, half the barriers).
@@ -113,13 +128,12 @@ __device__ __forceinline__ void stockham_pass2(const float2* __restrict__ x0, fl
     }
     __syncthreads();
 }
-// forward FFTs of a0[480] and a1[480]; results land in b0 and b1.
+// forward FFTs of a0[480] and a1[480]; results land back in a0 and a1.
 __device__ void fft480x2(float2* a0, float2* b0, float2* a1, float2* b1, const float2* tw) {
     stockham_pass2<4, 480, 1>(a0, b0, a1, b1, tw);
     stockham_pass2<4, 120, 4>(b0, a0, b1, a1, tw);
     stockham_pass2<5, 30, 16>(a0, b0, a1, b1, tw);
-    stockham_pass2<3, 6, 80>(b0, a0, b1, a1, tw);
-    stockham_pass2<2, 2, 240>(a0, b0, a1, b1, tw);
+    stockham_pass2<6, 6, 80>(b0, a0, b1, a1, tw);
 }
 
 // Band-weighted sums (src/lib.rs:65-82), balanced two-stage reduction driven by DeviceTables::bt_*.
@@ -289,8 +303,8 @@ __global__ void __launch_bounds__(ST, 10) analysis_kernel(BatchBuffers bb, const
     fft480x2(xa, xb, pa, pb, tab->tw480);
     float2* xs = xa;
     float2* ps = pa;
-    rfft_post(xb, xs, tab);
-    rfft_post(pb, ps, tab);
+    rfft_post(xa, xs, tab);  // in place: bins k and 480 - k are read and written by the same thread
+    rfft_post(pa, ps, tab);
     __syncthreads();
 
     float2* Xg = bb.X + (size_t)s * FREQ_SIZE;
@@ -531,7 +545,7 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
     fft480(fa_, fb_, tab->tw480);
     float* sm = bb.synth_mem + (size_t)s * FRAME_SIZE;
     TOut* o = out + (long)s * stream_stride;
-    // time samples 4q..4q+3 = (re, -im) of fb_[2q], fb_[2q+1]; first half -> output (+ overlap memory),
+    // time samples 4q..4q+3 = (re, -im) of fa_[2q], fa_[2q+1] (the four-pass FFT ends in its input buffer); first half -> output (+ overlap memory),
     // second half -> new overlap memory.  Vector stores when the caller's rows are aligned for them.
     const bool o_vec = sample_stride == 1 && ((reinterpret_cast<uintptr_t>(o) & (4 * sizeof(TOut) - 1)) == 0);
     const long ss = sample_stride;
@@ -539,7 +553,7 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
     for (int it = 0; it < 2; it++) {
         const int q = tid + it * ST;
         if (q < WINDOW_SIZE / 4) {
-            const float4 z = reinterpret_cast<const float4*>(fb_)[q];
+            const float4 z = reinterpret_cast<const float4*>(fa_)[q];
             const float4 w = __ldg(reinterpret_cast<const float4*>(tab->window) + q);
             const float4 v = make_float4((z.x * 0.5f) * w.x, (-z.y * 0.5f) * w.y, (z.z * 0.5f) * w.z, (-z.w * 0.5f) * w.w);
             if (q < FRAME_SIZE / 4) {
@@ -563,12 +577,12 @@ __global__ void __launch_bounds__(ST) synthesis_kernel(BatchBuffers bb, const De
                     }
                 }
             } else {
-                reinterpret_cast<float4*>(fa_)[q - FRAME_SIZE / 4] = v;  // staged: sm is still being read by other threads
+                reinterpret_cast<float4*>(fb_)[q - FRAME_SIZE / 4] = v;  // staged: sm is still being read by other threads
             }
         }
     }
     __syncthreads();
-    for (int q = tid; q < FRAME_SIZE / 4; q += ST) reinterpret_cast<float4*>(sm)[q] = reinterpret_cast<const float4*>(fa_)[q];
+    for (int q = tid; q < FRAME_SIZE / 4; q += ST) reinterpret_cast<float4*>(sm)[q] = reinterpret_cast<const float4*>(fb_)[q];
     if (tid == 0 && vad_out) vad_out[s] = silent ? 0.0f : vad_in;
 }
 

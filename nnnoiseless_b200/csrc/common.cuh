@@ -55,6 +55,7 @@ struct DeviceTables {
     float bt_w[800];
     int16_t bt_lane_start[BT_LANES + 1];
     int16_t bt_band_lane[NB_BANDS + 1];
+    int16_t bt_lane_band[BT_LANES];  // band of each lane (lanes of one band are contiguous)
 };
 
 // One dense or GRU layer as laid out on the device: int8 weights expanded to f32, output dimension padded

@@ -128,7 +128,10 @@ void build_tables(DeviceTables* t) {
             }
         const int n = nterm - first, lanes = (n + 8) / 9;  // <= 9 terms per lane; totals exactly BT_LANES lanes
         t->bt_band_lane[b] = (int16_t)lane;
-        for (int l = 0; l < lanes; l++) t->bt_lane_start[lane++] = (int16_t)(first + (int)((long)n * l / lanes));
+        for (int l = 0; l < lanes; l++) {
+            t->bt_lane_band[lane] = (int16_t)b;
+            t->bt_lane_start[lane++] = (int16_t)(first + (int)((long)n * l / lanes));
+        }
     }
     t->bt_band_lane[NB_BANDS] = (int16_t)lane;
     t->bt_lane_start[lane] = (int16_t)nterm;

@@ -136,40 +136,66 @@ __device__ void fft480x2(float2* a0, float2* b0, float2* a1, float2* b1, const f
     stockham_pass2<6, 6, 80>(b0, a0, b1, a1, tw);
 }
 
-// Band-weighted sums (src/lib.rs:65-82), balanced two-stage reduction driven by DeviceTables::bt_*.
+// Band-weighted sums (src/lib.rs:65-82) driven by DeviceTables::bt_*: the 800 weighted terms are dealt to BT_LANES = 96
+// lanes (3 warps), <= 9 CONSECUTIVE bins of one band each (straight-line, predicated); the lanes of a band are
+// contiguous, so a segmented shuffle reduction leaves each band's sum (per warp) in its first lane; bands that straddle a
+// warp boundary are completed from the per-warp partials in a fixed order (deterministic).
 // NS = 3: ex = |X|^2, ep = |P|^2, exp = Re(X conj P) in one sweep (x, p: spectra in shared memory);
-// NS = 1: only |X|^2.  part: shared scratch [NS][BT_LANES].  All threads must call; contains two barriers.
+// NS = 1: only |X|^2.  part: shared scratch [NS][3][NB_BANDS].  All threads must call; contains two barriers.
 template <int NS>
 __device__ __forceinline__ void band_sums(const float2* xs, const float2* ps, const DeviceTables* __restrict__ tab, float* part,
                                           float* o0, float* o1, float* o2) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    static_assert(BT_LANES == 96, "three warps of band lanes");
     if (tid < BT_LANES) {
-        const int t0 = tab->bt_lane_start[tid], t1 = tab->bt_lane_start[tid + 1];
+        const int t0 = tab->bt_lane_start[tid], n = tab->bt_lane_start[tid + 1] - t0;
+        const int bin0 = tab->bt_bin[t0];
+        const int band = tab->bt_lane_band[tid];
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-        for (int t = t0; t < t1; t++) {
-            const int bin = tab->bt_bin[t];
-            const float w = __ldg(&tab->bt_w[t]);
-            const float2 x = xs[bin];
-            a0 = fmaf(w, x.x * x.x + x.y * x.y, a0);
-            if (NS == 3) {
-                const float2 p = ps[bin];
-                a1 = fmaf(w, p.x * p.x + p.y * p.y, a1);
-                a2 = fmaf(w, x.x * p.x + x.y * p.y, a2);
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            if (i < n) {
+                const float w = __ldg(&tab->bt_w[t0 + i]);
+                const float2 x = xs[bin0 + i];
+                a0 = fmaf(w, x.x * x.x + x.y * x.y, a0);
+                if (NS == 3) {
+                    const float2 p = ps[bin0 + i];
+                    a1 = fmaf(w, p.x * p.x + p.y * p.y, a1);
+                    a2 = fmaf(w, x.x * p.x + x.y * p.y, a2);
+                }
             }
         }
-        part[tid] = a0;
-        if (NS == 3) {
-            part[BT_LANES + tid] = a1;
-            part[2 * BT_LANES + tid] = a2;
+        // segmented reduction towards the first lane of each band within the warp
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int ob = __shfl_down_sync(0xffffffffu, band, off);
+            const float v0 = __shfl_down_sync(0xffffffffu, a0, off);
+            const float v1 = NS == 3 ? __shfl_down_sync(0xffffffffu, a1, off) : 0.0f;
+            const float v2 = NS == 3 ? __shfl_down_sync(0xffffffffu, a2, off) : 0.0f;
+            if (lane + off < 32 && ob == band) {
+                a0 += v0;
+                if (NS == 3) {
+                    a1 += v1;
+                    a2 += v2;
+                }
+            }
+        }
+        const int prev = __shfl_up_sync(0xffffffffu, band, 1);
+        if (lane == 0 || prev != band) {
+            part[warp * NB_BANDS + band] = a0;
+            if (NS == 3) {
+                part[(3 + warp) * NB_BANDS + band] = a1;
+                part[(6 + warp) * NB_BANDS + band] = a2;
+            }
         }
     }
     __syncthreads();
     if (tid < NS * 32) {
         const int which = tid >> 5, b = tid & 31;
         if (b < NB_BANDS) {
-            const int l0 = tab->bt_band_lane[b], l1 = tab->bt_band_lane[b + 1];
+            const int w0 = tab->bt_band_lane[b] >> 5, w1 = (tab->bt_band_lane[b + 1] - 1) >> 5;
             float acc = 0.0f;
-            for (int l = l0; l < l1; l++) acc += part[which * BT_LANES + l];
+            for (int w = w0; w <= w1; w++) acc += part[(which * 3 + w) * NB_BANDS + b];
             if (b == 0 || b == NB_BANDS - 1) acc *= 2.0f;
             float* o = which == 0 ? o0 : (which == 1 ? o1 : o2);
             o[b] = acc;

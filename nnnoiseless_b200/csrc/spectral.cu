@@ -304,11 +304,10 @@ __global__ void __launch_bounds__(ST, 10) analysis_kernel(BatchBuffers bb, const
     __shared__ __align__(16) float2 pa[FREQ_SIZE + 1];  // P: the same for the pitch-lagged window
     __shared__ __align__(16) float2 pb[480];
     __shared__ float part[3 * BT_LANES];
-    __shared__ float s_ex[NB_BANDS], s_ep[NB_BANDS], s_exp[NB_BANDS], s_tmp[NB_BANDS], s_ly[NB_BANDS];
+    __shared__ float s_ex[NB_BANDS], s_ep[NB_BANDS], s_exp[NB_BANDS];
     __shared__ float s_feat[NB_FEATURES];
     __shared__ float s_ceps[CEPS_MEM][NB_BANDS];
     __shared__ float s_dist[CEPS_MEM][CEPS_MEM];
-    __shared__ int s_flag;
 
     const int s = blockIdx.x, tid = threadIdx.x;
     const float* h = bb.hist + (size_t)s * HIST_CAP;
@@ -339,98 +338,111 @@ __global__ void __launch_bounds__(ST, 10) analysis_kernel(BatchBuffers bb, const
     for (int k = tid; k < NB_BINS_BANDED; k += ST) Pg[k] = ps[k];
     band_sums<3>(xs, ps, tab, part, s_ex, s_ep, s_exp);
 
-    // ---- features ----
-    if (tid < NB_BANDS) {
-        s_exp[tid] = s_exp[tid] / sqrtf(0.001f + s_ex[tid] * s_ep[tid]);
-        bb.ex[(size_t)s * NB_BANDS + tid] = s_ex[tid];
-        bb.ep[(size_t)s * NB_BANDS + tid] = s_ep[tid];
-        bb.exp[(size_t)s * NB_BANDS + tid] = s_exp[tid];
+    // ---- features (src/features.rs:134-219): 22 bands = one warp, lane = band; no block barriers from here on ----
+    if (tid >= 32) return;
+    const int lane = tid;
+    const bool bl = lane < NB_BANDS;
+    const float ex = bl ? s_ex[lane] : 0.0f, ep = bl ? s_ep[lane] : 0.0f;
+    const float xpn = bl ? s_exp[lane] / sqrtf(0.001f + ex * ep) : 0.0f;
+    if (bl) {
+        bb.ex[(size_t)s * NB_BANDS + lane] = ex;
+        bb.ep[(size_t)s * NB_BANDS + lane] = ep;
+        bb.exp[(size_t)s * NB_BANDS + lane] = xpn;
     }
-    __syncthreads();
-    const double dct_scale = 0.30151134457776362265;  // sqrt(2/22), src/lib.rs:146
-    if (tid < NB_BANDS) {
-        float sum = 0.0f;
-        for (int j = 0; j < NB_BANDS; j++) sum += s_exp[j] * tab->dct[j * NB_BANDS + tid];
-        s_tmp[tid] = (float)((double)sum * dct_scale);
-    }
-    if (tid >= 32 && tid < 64) {  // another warp: log band energies, sequential follower (src/features.rs:147-158)
-        const int i = tid - 32;
-        float lg = (i < NB_BANDS) ? log10f(1e-2f + s_ex[i]) : 0.0f;
-        float exi = (i < NB_BANDS) ? s_ex[i] : 0.0f;
-        float log_max = -2.0f, follow = -2.0f, e = 0.0f;
-#pragma unroll
-        for (int k = 0; k < NB_BANDS; k++) {
-            float ly = fmaxf(fmaxf(__shfl_sync(0xffffffffu, lg, k), log_max - 7.0f), follow - 1.5f);
-            if (i == k) s_ly[k] = ly;
-            log_max = fmaxf(log_max, ly);
-            follow = fmaxf(follow - 1.5f, ly);
-            e += __shfl_sync(0xffffffffu, exi, k);
-        }
-        if (i == 0) s_flag = (e < 0.04f) ? 1 : 0;
-    }
-    __syncthreads();
-    const int silent = s_flag;
-    float* featg = bb.features + (size_t)s * NB_FEATURES;
-    if (silent) {
-        if (tid < NB_FEATURES) featg[tid] = 0.0f;
-        if (tid == 0) bb.silence[s] = 1;
-        return;
-    }
-    // ceps ring
+    // cepstral ring (8 x 22): 6 elements per lane, in flight while the log energies are computed
     float* cg = bb.ceps_mem + (size_t)s * CEPS_MEM * NB_BANDS;
     const int mem_id = bb.ceps_id[s];
-    for (int i = tid; i < CEPS_MEM * NB_BANDS; i += ST) (&s_ceps[0][0])[i] = cg[i];
-    if (tid < NB_BANDS) {
-        float sum = 0.0f;
-        for (int j = 0; j < NB_BANDS; j++) sum += s_ly[j] * tab->dct[j * NB_BANDS + tid];
-        float v = (float)((double)sum * dct_scale);
-        if (tid == 0) v -= 12.0f;
-        if (tid == 1) v -= 4.0f;
-        s_feat[tid] = v;
+    float cr[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cr[k] = (lane + 32 * k < CEPS_MEM * NB_BANDS) ? cg[lane + 32 * k] : 0.0f;
+    // log band energies with the sequential follower (src/features.rs:147-158) and the silence test (:160)
+    const float lg = bl ? log10f(1e-2f + ex) : 0.0f;
+    float ly = 0.0f, log_max = -2.0f, follow = -2.0f, e = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NB_BANDS; k++) {
+        const float v = fmaxf(fmaxf(__shfl_sync(0xffffffffu, lg, k), log_max - 7.0f), follow - 1.5f);
+        if (lane == k) ly = v;
+        log_max = fmaxf(log_max, v);
+        follow = fmaxf(follow - 1.5f, v);
+        e += __shfl_sync(0xffffffffu, ex, k);
     }
-    __syncthreads();
-    if (tid < NB_BANDS) {
-        s_ceps[mem_id][tid] = s_feat[tid];
-        cg[mem_id * NB_BANDS + tid] = s_feat[tid];
+    float* featg = bb.features + (size_t)s * NB_FEATURES;
+    if (e < 0.04f) {  // silent frame: zero features, cepstral ring untouched (src/features.rs:160-166)
+        featg[lane] = 0.0f;
+        if (lane + 32 < NB_FEATURES) featg[lane + 32] = 0.0f;
+        if (lane == 0) bb.silence[s] = 1;
+        return;
     }
-    __syncthreads();
-    if (tid < NB_DELTA_CEPS) {
+    // both DCTs (src/lib.rs:139-148) share the table: lane i accumulates output i over j in order
+    const double dct_scale = 0.30151134457776362265;  // sqrt(2/22), src/lib.rs:146
+    float sum_ly = 0.0f, sum_xp = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NB_BANDS; j++) {
+        const float d = bl ? __ldg(&tab->dct[j * NB_BANDS + lane]) : 0.0f;
+        sum_ly += __shfl_sync(0xffffffffu, ly, j) * d;
+        sum_xp += __shfl_sync(0xffffffffu, xpn, j) * d;
+    }
+    float ceps = (float)((double)sum_ly * dct_scale);
+    float pcor = (float)((double)sum_xp * dct_scale);
+    if (lane == 0) {
+        ceps -= 12.0f;
+        pcor -= 1.3f;
+    }
+    if (lane == 1) {
+        ceps -= 4.0f;
+        pcor -= 0.9f;
+    }
+    // ring -> shared memory, with the new row in place
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (lane + 32 * k < CEPS_MEM * NB_BANDS) (&s_ceps[0][0])[lane + 32 * k] = cr[k];
+    __syncwarp();
+    if (bl) {
+        s_ceps[mem_id][lane] = ceps;
+        cg[mem_id * NB_BANDS + lane] = ceps;
+        s_feat[lane] = ceps;
+    }
+    __syncwarp();
+    if (lane < NB_DELTA_CEPS) {
         const int c1 = (mem_id < 1) ? CEPS_MEM + mem_id - 1 : mem_id - 1;
         const int c2 = (mem_id < 2) ? CEPS_MEM + mem_id - 2 : mem_id - 2;
-        float a = s_ceps[mem_id][tid], b = s_ceps[c1][tid], c = s_ceps[c2][tid];
-        s_feat[tid] = a + b + c;
-        s_feat[NB_BANDS + tid] = a - c;
-        s_feat[NB_BANDS + NB_DELTA_CEPS + tid] = a - 2.0f * b + c;
-        float v = s_tmp[tid];
-        if (tid == 0) v -= 1.3f;
-        if (tid == 1) v -= 0.9f;
-        s_feat[NB_BANDS + 2 * NB_DELTA_CEPS + tid] = v;
+        const float a = s_ceps[mem_id][lane], b = s_ceps[c1][lane], c = s_ceps[c2][lane];
+        s_feat[lane] = a + b + c;
+        s_feat[NB_BANDS + lane] = a - c;
+        s_feat[NB_BANDS + NB_DELTA_CEPS + lane] = a - 2.0f * b + c;
+        s_feat[NB_BANDS + 2 * NB_DELTA_CEPS + lane] = pcor;
     }
-    if (tid >= 64 && tid < 128) {
-        int i = (tid - 64) >> 3, j = (tid - 64) & 7;
+    // spectral variability (src/features.rs:199-216): pairwise squared distances of the 8 ring rows, two pairs per lane
+#pragma unroll
+    for (int h2 = 0; h2 < 2; h2++) {
+        const int pr = lane + 32 * h2, i = pr >> 3, j = pr & 7;
         float dist = 0.0f;
+#pragma unroll
         for (int k = 0; k < NB_BANDS; k++) {
-            float t = s_ceps[i][k] - s_ceps[j][k];
+            const float t = s_ceps[i][k] - s_ceps[j][k];
             dist += t * t;
         }
         s_dist[i][j] = dist;
     }
-    __syncthreads();
-    if (tid == 0) {
-        float sv = 0.0f;
-        for (int i = 0; i < CEPS_MEM; i++) {
-            float md = 1e15f;
-            for (int j = 0; j < CEPS_MEM; j++)
-                if (j != i) md = fminf(md, s_dist[i][j]);
-            sv += md;
-        }
+    __syncwarp();
+    float md = 1e15f;
+    if (lane < CEPS_MEM) {
+#pragma unroll
+        for (int j = 0; j < CEPS_MEM; j++)
+            if (j != lane) md = fminf(md, s_dist[lane][j]);
+    }
+    float sv = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CEPS_MEM; i++) sv += __shfl_sync(0xffffffffu, md, i);  // i = 0..7 in order, like the reference
+    if (lane == 0) {
         s_feat[NB_BANDS + 3 * NB_DELTA_CEPS] = 0.01f * ((float)pitch - 300.0f);
         s_feat[NB_BANDS + 3 * NB_DELTA_CEPS + 1] = sv / (float)CEPS_MEM - 2.1f;
         bb.ceps_id[s] = (mem_id + 1 == CEPS_MEM) ? 0 : mem_id + 1;
         bb.silence[s] = 0;
     }
-    __syncthreads();
-    if (tid < NB_FEATURES) featg[tid] = s_feat[tid];
+    __syncwarp();
+    featg[lane] = s_feat[lane];
+    if (lane + 32 < NB_FEATURES) featg[lane + 32] = s_feat[lane + 32];
 }
 
 cudaError_t launch_analysis(const BatchBuffers& b, const DeviceTables* tab, int slot, cudaStream_t st) {

@@ -17,9 +17,9 @@
 // shared-memory-bound inner products overlap the other's FP-bound cross-correlation and serial phases):
 //   P   [SB][868]  2x-decimated, LPC-whitened history (pitch_buf); row stride 868 = 16B aligned and
 //                  = 4 (mod 32) so that lane-per-stream float4 reads are bank-conflict free
-//   Y4  [SB][436]  its even samples (the 4x-decimated signal); later reused for the fine running
-//                  energies yn2 [SB][297] and then for yy_lookup [SB][387]
+//   Y4  [SB][436]  its even samples (the 4x-decimated signal); later reused for yy_lookup [SB][387]
 //   XC  [SB][149]  coarse cross-correlation      YN4 [SB][149]  coarse running energy
+//   CK  [SB][39]   fine running energy, one checkpoint every 8 lags (replayed where the fine search needs it)
 #include "common.cuh"
 
 namespace nnb {
@@ -53,7 +53,6 @@ constexpr int MIN_PERIOD2 = PITCH_MIN_PERIOD / 2;                      // 30
 constexpr int P_LD = 868;
 constexpr int Y4_LD = 436;
 constexpr int XC_LD = 149;
-constexpr int YN2_LD = 297;
 constexpr int YY_LD = 387;
 constexpr int IPR_LD = 31;
 constexpr int FX_LD = 11;
@@ -77,7 +76,7 @@ constexpr int CK_LD = 39;
 constexpr int OFF_CK = OFF_TASK + SB * 29;          // [SB][39]
 constexpr int SMEM_FLOATS = OFF_CK + SB * CK_LD;
 static_assert(CK_N <= CK_LD, "checkpoint row too short");
-static_assert(SB * YN2_LD <= SB * Y4_LD && SB * YY_LD <= SB * Y4_LD, "yn2 / yy must fit in the Y4 region");
+static_assert(YY_LD <= Y4_LD, "yy must fit in the Y4 region");
 static_assert(SMEM_FLOATS * 4 + 1024 <= 227 * 1024, "tile must fit in one SM");
 
 

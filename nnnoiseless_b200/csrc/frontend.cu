@@ -205,11 +205,6 @@ int rnnoise_denoise_files(int n_files, const char* const* in_paths, const char* 
         if (S > (1 << 28)) return set_error("too many channels in one call");
     }
 
-    // format errors above are reported even on a machine without a GPU; from here on CUDA is required
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error("no CUDA device available (this library has no CPU fallback)");
-    if (o.device >= 0) FCK(cudaSetDevice(o.device));
-
     // ---- position tables, one per distinct rate -------------------------------------------------------
     std::map<double, PosTable> tables;
     for (Job& j : jobs)
@@ -233,7 +228,12 @@ int rnnoise_denoise_files(int n_files, const char* const* in_paths, const char* 
 
     // ---- device: sources, tables, one chunk of interleaved frames in / out -----------------------------------
     Cleanup cl;
-    if (Tmax > 1) {
+    if (Tmax > 1) {  // inputs shorter than two frames produce no output (src/nnnoiseless.rs:319-327) and need no device
+        // format errors above are reported even on a machine without a GPU; from here on CUDA is required
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            return set_error("no CUDA device available (this library has no CPU fallback)");
+        if (o.device >= 0) FCK(cudaSetDevice(o.device));
         FCK(cudaStreamCreateWithFlags(&cl.st, cudaStreamNonBlocking));
         for (Job& j : jobs) {
             const size_t n = j.a.samples.size();

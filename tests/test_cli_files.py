@@ -131,6 +131,17 @@ def test_cli_argument_errors(tmp_path):
     assert subprocess.run([files.CLI_PATH, "--help"], capture_output=True).returncode == 0
 
 
+def test_cli_inputs_shorter_than_two_frames(tmp_path):
+    """The first frame's output is discarded (src/nnnoiseless.rs:319-327): < 960 samples in -> an empty but valid output."""
+    (tmp_path / "short.raw").write_bytes(bytes(2 * 700))
+    r = subprocess.run([files.CLI_PATH, str(tmp_path / "short.raw"), str(tmp_path / "o.wav")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    back, rate = oracle.decode_wav((tmp_path / "o.wav").read_bytes())
+    assert rate == 48000.0 and back.shape == (0, 1)
+    r = subprocess.run([files.CLI_PATH, str(tmp_path / "short.raw"), str(tmp_path / "o.raw")], capture_output=True, text=True)
+    assert r.returncode == 0 and (tmp_path / "o.raw").read_bytes() == b""
+
+
 def test_oracle_resampler_properties():
     n = np.arange(44100)
     x = (10000 * np.sin(2 * np.pi * 1000 * n / 44100)).astype(np.float32)

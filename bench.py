@@ -125,6 +125,16 @@ def synth_on_device(torch, B, T, device, seed):
     return x
 
 
+# BASELINE.json "metric": "48kHz mono frames/sec (480-sample) at 1/2/4/8 B200; %HBM roofline; vs Rust CPU" -- the
+# throughput part is the line's value, the other two parts are the `roofline` and `cpu_baseline` objects of the line.
+METRIC = "48kHz mono frames/sec (480-sample)"
+
+
+def workload_name(streams_per_gpu, frames):
+    """config.workload, identical for both arms (BASELINE.json configs[1] when streams_per_gpu = 4096)."""
+    return "configs[1]: batch=%d independent mono streams per GPU x %d frames per step, built-in model" % (streams_per_gpu, frames)
+
+
 def host_threads():
     """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arm must not obey that)."""
     try:
@@ -168,11 +178,10 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = frames / dt
     line = {
-        "impl": "reference", "metric": "48kHz mono 480-sample frames/sec", "value": value, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: batch=%d independent mono streams x %d frames, built-in model" % (args.streams, T),
-                   "streams_per_gpu": args.streams, "frames_per_step": T},
+        "config": {"workload": workload_name(args.streams, T), "streams_per_gpu": args.streams, "frames_per_step": T},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": "%d streams x %d frames per step, oracle/nno_oracle.c (C restatement; no rustc in image), "
                                    "OpenMP one stream per thread" % (n, T)},
@@ -361,11 +370,10 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": "48kHz mono 480-sample frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: batch=%d independent mono streams per GPU x %d frames per step, built-in model"
-                                   % (B, T),
+            "config": {"workload": workload_name(B, T),
                        "streams_per_gpu": B, "frames_per_step": T, "parallelism": "streams sharded x%d, no data-path collective" % world,
                        "l2_policy": "inputs larger than L2: each step streams %.0f MB in + %.0f MB out through HBM"
                                     % (T * B * 1920 / 1e6, T * B * 1920 / 1e6)},

@@ -53,13 +53,22 @@ def test_builtin_model_is_weights_rnn(builtin_bytes):
 
 
 def test_text_model_conversion(sh_bytes):
-    """train/convert_rnnoise.py:18-29 semantics on a synthetic text file built from the fixture."""
-    ints = np.frombuffer(sh_bytes, dtype=np.int8)
-    text = "rnnoise-nu model file version 1\n" + " ".join(str(int(v)) for v in ints) + "\n"
+    """N3 (train/convert_rnnoise.py:18-29): the reference's own text fixture test_data/sh.rnnn (committed as
+    tests/golden/sh.rnnn) through rnnoise_model_from_text equals the image the independent restatement of the
+    converter (tests/golden/make_sh_rnn.py) produces from it, byte for byte."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_sh_rnn", os.path.join(ROOT, "tests", "golden", "make_sh_rnn.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(ROOT, "tests", "golden", "sh.rnnn")).read()
+    assert gen.convert(text) == sh_bytes and len(sh_bytes) == 87521  # the committed binary fixture is the generator's output
     m = nb.RnnModel.from_text(text)
     assert m is not None and m.to_bytes() == sh_bytes
+    assert oracle.model_accepts(sh_bytes)
+    # negative numbers wrap like python's int(s) % 256; junk is rejected
     assert nb.RnnModel.from_text("wrong header\n1 2 3") is None
     assert nb.RnnModel.from_text("rnnoise-nu model file version 1\n1 2 x") is None
+    assert nb.RnnModel.from_text(text[: len(text) // 2]) is None  # truncated image no longer chains (src/rnn.rs:196-222)
 
 
 def test_model_from_file_takes_over_file(tmp_path, builtin_bytes):

@@ -32,7 +32,7 @@ C_ABI_SYMBOLS = [
     "rnnoise_batch_process_device", "rnnoise_batch_process_device_pcm16", "rnnoise_batch_process_device_strided",
     "rnnoise_batch_process_host",
     "rnnoise_batch_process_pcm16_host",
-    "rnnoise_batch_get_taps", "rnnoise_batch_profile_step", "rnnoise_kernel_name",
+    "rnnoise_batch_get_taps", "rnnoise_batch_profile_step", "rnnoise_kernel_name", "rnnoise_batch_pitch_stats",
     "rnnoise_train_create", "rnnoise_train_destroy", "rnnoise_train_lanes", "rnnoise_train_set_params",
     "rnnoise_train_band_lp", "rnnoise_train_process_host", "rnnoise_train_process_device",
     "rnnoise_denoise_file", "rnnoise_denoise_files", "rnnoise_resample_host",
@@ -94,6 +94,8 @@ def lib():
     L.rnnoise_batch_process_pcm16_host.argtypes = [vp, vp, vp, vp, ci]
     L.rnnoise_batch_get_taps.restype = ci
     L.rnnoise_batch_get_taps.argtypes = [vp, vp, vp, vp, vp]
+    L.rnnoise_batch_pitch_stats.restype = ci
+    L.rnnoise_batch_pitch_stats.argtypes = [vp, vp]
     L.rnnoise_batch_profile_step.restype = ci
     L.rnnoise_batch_profile_step.argtypes = [vp, vp, vp, vp, C.c_long, vp, vp, ci]
     L.rnnoise_train_create.restype = vp
@@ -271,6 +273,13 @@ class DenoiseBatch:
         if n < 0:
             raise NnnoiselessError(last_error())
         return {lib().rnnoise_kernel_name(i).decode(): float(ms[i]) for i in range(n)}
+
+    def pitch_stats(self):
+        """Cumulative pitch-kernel certification counters: dict(coarse_exact, ladder_exact, stream_frames)."""
+        out = (C.c_ulonglong * 3)()
+        if lib().rnnoise_batch_pitch_stats(self._h, out) != 0:
+            raise NnnoiselessError(last_error())
+        return dict(coarse_exact=int(out[0]), ladder_exact=int(out[1]), stream_frames=int(out[2]))
 
     def taps(self):
         """Intermediates of the most recent frame: dict(pitch, silence, features, gains)."""

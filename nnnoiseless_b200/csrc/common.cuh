@@ -124,6 +124,9 @@ struct BatchBuffers {
     int32_t* pitch;      // [B]
     float* gains;        // [B][22]  raw RNN gains
     float* vad;          // [B]
+    // pitch_kernel statistics: [0] streams whose coarse search was recomputed exactly, [1] streams whose sub-harmonic
+    // ladder was, [2] stream-frames processed (cumulative since the handle was created)
+    unsigned long long* pitch_stats;
 };
 
 // ---- training-data rows (src/training.rs): per-lane simulator parameters and state --------------------
@@ -142,11 +145,28 @@ struct TrainBuffers {
     int32_t* cutoff;          // [PIPE_DEPTH][L]  band_gain_cutoff before the silence override
 };
 
+// The caller's current device is restored when an entry point returns (a multi-GPU host thread, e.g. PyTorch with
+// tensors elsewhere, must not find its device switched behind its back).
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) : want(dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ---- launchers (one per translation unit) ------------------------------------------------------
 // exact.cu (compiled with -fmad=false: bit-exact pitch path)
 cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, long stream_stride, long sample_stride, int slot,
                              cudaStream_t st);
-cudaError_t launch_pitch(const BatchBuffers& b, int slot, cudaStream_t st);
+// force_exact: every stream takes the order-exact recomputation paths (NNB_PITCH_EXACT=1: the test reference)
+cudaError_t launch_pitch(const BatchBuffers& b, int slot, bool force_exact, cudaStream_t st);
 // spectral.cu
 cudaError_t launch_analysis(const BatchBuffers& b, const DeviceTables* tab, int slot, cudaStream_t st);
 cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride, long sample_stride,

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory>
+#include <sys/stat.h>
 #include <string>
 #include <vector>
 
@@ -149,7 +151,10 @@ long rnnoise_resample_host(float* out, long cap, const float* in, long n_in, int
     if (!out || !in || channels < 1 || n_in < 0 || cap < 0) return set_error("rnnoise_resample_host: bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error("no CUDA device available (this library has no CPU fallback)");
-    if (device >= 0) FCK(cudaSetDevice(device));
+    int cur_dev = 0;
+    FCK(cudaGetDevice(&cur_dev));
+    DeviceGuard guard(device >= 0 ? device : cur_dev);
+    if (guard.err != cudaSuccess) return set_error("cudaSetDevice failed");
     PosTable t;
     build_pos_table(ratio, n_in, &t);
     const long K = std::min<long>((long)t.m.size(), cap);
@@ -172,6 +177,13 @@ long rnnoise_resample_host(float* out, long cap, const float* in, long n_in, int
     return K;
 }
 
+static bool same_file(const char* a, const char* b) {
+    if (std::string(a) == b) return true;
+    struct stat sa, sb;
+    if (stat(a, &sa) != 0 || stat(b, &sb) != 0) return false;
+    return sa.st_dev == sb.st_dev && sa.st_ino == sb.st_ino;
+}
+
 int rnnoise_denoise_files(int n_files, const char* const* in_paths, const char* const* out_paths, const RNNoiseFileOptions* opt) {
     if (n_files < 0 || (n_files > 0 && (!in_paths || !out_paths))) return set_error("rnnoise_denoise_files: bad argument");
     if (n_files == 0) return 0;
@@ -182,6 +194,15 @@ int rnnoise_denoise_files(int n_files, const char* const* in_paths, const char* 
     const int raw_channels = o.channels > 0 ? o.channels : 1;               // :271
 
     // ---- decode (host) ----------------------------------------------------------------------------
+    // One file: like the reference, the output is created before the input is parsed (src/nnnoiseless.rs:251-258).
+    // A batch (additive mode) must not amplify that: an output that is also an input of the batch is refused, every input
+    // is decoded first, and only then are the outputs created -- a malformed file leaves the other files untouched.
+    const bool batch_mode = n_files > 1;
+    if (batch_mode)
+        for (int i = 0; i < n_files; i++)
+            for (int k = 0; k < n_files; k++)
+                if (same_file(out_paths[i], in_paths[k]))
+                    return set_error(std::string("output file \"") + out_paths[i] + "\" is also an input of this batch");
     std::vector<Job> jobs((size_t)n_files);
     std::vector<bool> wav_out((size_t)n_files);
     long S = 0;
@@ -193,9 +214,11 @@ int rnnoise_denoise_files(int n_files, const char* const* in_paths, const char* 
         FILE* probe = fopen(in.c_str(), "rb");
         if (!probe) return set_error("Failed to open input file \"" + in + "\"");  // :251-253
         fclose(probe);
-        FILE* created = fopen(outp.c_str(), "wb");  // the reference creates the output before it parses the input (:255-258)
-        if (!created) return set_error("Failed to open output file \"" + outp + "\"");
-        fclose(created);
+        if (!batch_mode) {
+            FILE* created = fopen(outp.c_str(), "wb");  // the reference creates the output before it parses the input (:255-258)
+            if (!created) return set_error("Failed to open output file \"" + outp + "\"");
+            fclose(created);
+        }
         Job& j = jobs[i];
         const bool ok = wav_in ? read_wav_file(in, &j.a, &err) : read_raw_file(in, raw_channels, raw_rate, &j.a, &err);
         if (!ok) return set_error(err);
@@ -204,6 +227,12 @@ int rnnoise_denoise_files(int n_files, const char* const* in_paths, const char* 
         S += j.a.channels;
         if (S > (1 << 28)) return set_error("too many channels in one call");
     }
+    if (batch_mode)
+        for (int i = 0; i < n_files; i++) {
+            FILE* created = fopen(out_paths[i], "wb");
+            if (!created) return set_error(std::string("Failed to open output file \"") + out_paths[i] + "\"");
+            fclose(created);
+        }
 
     // ---- position tables, one per distinct rate -------------------------------------------------------
     std::map<double, PosTable> tables;
@@ -227,13 +256,17 @@ int rnnoise_denoise_files(int n_files, const char* const* in_paths, const char* 
     }
 
     // ---- device: sources, tables, one chunk of interleaved frames in / out -----------------------------------
+    std::unique_ptr<DeviceGuard> guard;  // declared before `cl`: the device stays selected while cl's destructor frees
     Cleanup cl;
     if (Tmax > 1) {  // inputs shorter than two frames produce no output (src/nnnoiseless.rs:319-327) and need no device
         // format errors above are reported even on a machine without a GPU; from here on CUDA is required
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
             return set_error("no CUDA device available (this library has no CPU fallback)");
-        if (o.device >= 0) FCK(cudaSetDevice(o.device));
+        int cur_dev = 0;
+        FCK(cudaGetDevice(&cur_dev));
+        guard.reset(new DeviceGuard(o.device >= 0 ? o.device : cur_dev));
+        if (guard->err != cudaSuccess) return set_error("cudaSetDevice failed");
         FCK(cudaStreamCreateWithFlags(&cl.st, cudaStreamNonBlocking));
         for (Job& j : jobs) {
             const size_t n = j.a.samples.size();

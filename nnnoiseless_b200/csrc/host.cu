@@ -50,6 +50,10 @@ void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::me
 
 namespace {
 
+#define ON_DEVICE(dev)                                                   \
+    DeviceGuard guard__(dev);                                            \
+    if (guard__.err != cudaSuccess) return fail("cudaSetDevice", guard__.err)
+
 #define CK(call)                                         \
     do {                                                 \
         cudaError_t e__ = (call);                        \
@@ -360,16 +364,18 @@ struct RNNoiseBatch {
     UploadedMma umm;
     bool rnn_fp32 = false;  // NNB_RNN_FP32=1: CUDA-core FP32 GRU kernel instead of the tensor-core one (debug / comparison)
     bool serial = false;    // NNB_SERIAL=1: all stages on one stream (debug / comparison)
+    bool pitch_exact = false;  // NNB_PITCH_EXACT=1: every stream takes the pitch kernel's order-exact recomputation paths
     unsigned long long frame = 0;  // frames processed so far (ring slot = frame % HIST_SLOTS, set = frame % PIPE_DEPTH)
-    // host-call staging
-    float* stage_in = nullptr;
-    float* stage_out = nullptr;
+    // host-call staging: kStageSlots frames of device memory, recycled while a call of any length streams through
+    // (sized for the sample type in use only: float or int16)
+    char* stage_in = nullptr;
+    char* stage_out = nullptr;
     float* stage_vad = nullptr;
-    short* stage_pcm_in = nullptr;
-    short* stage_pcm_out = nullptr;
-    int stage_frames = 0;
-    bool stage_has_pcm = false;
+    size_t stage_bytes = 0;  // per buffer
+    cudaEvent_t ev_out[8];   // D2H copy of the frame that last used staging slot k
+    int slot_ev[8];          // event-ring index of the frame that last used staging slot k
 };
+constexpr int kStageSlots = 8;  // >= PIPE_DEPTH frames in the kernels + frames in the two copy engines
 
 namespace {
 
@@ -448,6 +454,7 @@ int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) 
         for (int k = 0; k < kEvRing; k++) CK(cudaEventCreateWithFlags(&b->ev[i][k], cudaEventDisableTiming));
     for (int k = 0; k < kEvRing; k++) CK(cudaEventCreateWithFlags(&b->ev_in[k], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_call, cudaEventDisableTiming));
+    for (int k = 0; k < kStageSlots; k++) CK(cudaEventCreateWithFlags(&b->ev_out[k], cudaEventDisableTiming));
     b->events_ok = true;
     const size_t B = (size_t)n_streams, D = PIPE_DEPTH;
     BatchBuffers& u = b->buf;
@@ -461,6 +468,8 @@ int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) 
         b->rnn_fp32 = e1 && e1[0] == '1';
         const char* e2 = getenv("NNB_SERIAL");
         b->serial = e2 && e2[0] == '1';
+        const char* e3 = getenv("NNB_PITCH_EXACT");
+        b->pitch_exact = e3 && e3[0] == '1';
     }
     const int SS = b->um.dm.state_size;
     if (dalloc(b, &u.hist, B * HIST_CAP) || dalloc(b, &u.hp_mem, B * 2) || dalloc(b, &u.synth_mem, B * FRAME_SIZE) ||
@@ -469,8 +478,9 @@ int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) 
         dalloc(b, &u.X, D * B * FREQ_SIZE) || dalloc(b, &u.P, D * B * NB_BINS_BANDED) || dalloc(b, &u.ex, D * B * NB_BANDS) ||
         dalloc(b, &u.ep, D * B * NB_BANDS) || dalloc(b, &u.exp, D * B * NB_BANDS) || dalloc(b, &u.features, D * B * NB_FEATURES) ||
         dalloc(b, &u.silence, D * B) || dalloc(b, &u.pitch, D * B) || dalloc(b, &u.gains, D * B * NB_BANDS) ||
-        dalloc(b, &u.vad, D * B) || dalloc(b, &b->d_tab, 1))
+        dalloc(b, &u.vad, D * B) || dalloc(b, &b->d_tab, 1) || dalloc(b, &u.pitch_stats, 3))
         return -1;
+    CK(cudaMemsetAsync(u.pitch_stats, 0, 3 * sizeof(unsigned long long), b->st[0]));
     DeviceTables* ht = new DeviceTables();
     build_tables(ht);
     cudaError_t ce = cudaMemcpyAsync(b->d_tab, ht, sizeof(DeviceTables), cudaMemcpyHostToDevice, b->st[0]);
@@ -484,16 +494,14 @@ void free_stage(RNNoiseBatch* b) {
     if (b->stage_in) cudaFree(b->stage_in);
     if (b->stage_out) cudaFree(b->stage_out);
     if (b->stage_vad) cudaFree(b->stage_vad);
-    if (b->stage_pcm_in) cudaFree(b->stage_pcm_in);
-    if (b->stage_pcm_out) cudaFree(b->stage_pcm_out);
-    b->stage_in = b->stage_out = b->stage_vad = nullptr;
-    b->stage_pcm_in = b->stage_pcm_out = nullptr;
-    b->stage_frames = 0;
+    b->stage_in = b->stage_out = nullptr;
+    b->stage_vad = nullptr;
+    b->stage_bytes = 0;
 }
 
 void batch_release(RNNoiseBatch* b) {
     if (!b) return;
-    cudaSetDevice(b->device);
+    DeviceGuard guard(b->device);
     for (int i = 0; i < kNumKernels; i++)
         if (b->st[i]) cudaStreamSynchronize(b->st[i]);
     if (b->c_in) cudaStreamSynchronize(b->c_in);
@@ -505,6 +513,7 @@ void batch_release(RNNoiseBatch* b) {
         for (int i = 0; i < kNumKernels; i++)
             for (int k = 0; k < kEvRing; k++) cudaEventDestroy(b->ev[i][k]);
         for (int k = 0; k < kEvRing; k++) cudaEventDestroy(b->ev_in[k]);
+        for (int k = 0; k < kStageSlots; k++) cudaEventDestroy(b->ev_out[k]);
         cudaEventDestroy(b->ev_call);
         b->events_ok = false;
     }
@@ -518,21 +527,15 @@ void batch_release(RNNoiseBatch* b) {
     b->c_in = b->c_out = nullptr;
 }
 
-int ensure_stage(RNNoiseBatch* b, int n_frames, bool pcm) {
-    if (n_frames > b->stage_frames || (pcm && !b->stage_has_pcm)) {
+int ensure_stage(RNNoiseBatch* b, bool pcm) {
+    const size_t need = (size_t)kStageSlots * b->n_streams * FRAME_SIZE * (pcm ? sizeof(short) : sizeof(float));
+    if (need > b->stage_bytes) {
         if (sync_all(b)) return -1;
-        const int nf = n_frames > b->stage_frames ? n_frames : b->stage_frames;
         free_stage(b);
-        size_t n = (size_t)nf * b->n_streams;
-        CK(cudaMalloc(&b->stage_in, n * FRAME_SIZE * sizeof(float)));
-        CK(cudaMalloc(&b->stage_out, n * FRAME_SIZE * sizeof(float)));
-        CK(cudaMalloc(&b->stage_vad, n * sizeof(float)));
-        if (pcm || b->stage_has_pcm) {
-            CK(cudaMalloc(&b->stage_pcm_in, n * FRAME_SIZE * sizeof(short)));
-            CK(cudaMalloc(&b->stage_pcm_out, n * FRAME_SIZE * sizeof(short)));
-            b->stage_has_pcm = true;
-        }
-        b->stage_frames = nf;
+        CK(cudaMalloc(&b->stage_in, need));
+        CK(cudaMalloc(&b->stage_out, need));
+        CK(cudaMalloc(&b->stage_vad, (size_t)kStageSlots * b->n_streams * sizeof(float)));
+        b->stage_bytes = need;
     }
     return 0;
 }
@@ -543,7 +546,7 @@ int launch_stage(RNNoiseBatch* b, int i, const BatchBuffers& v, void* out, const
                  long sample_stride, int slot, cudaStream_t s) {
     switch (i) {
         case 0: CK(launch_hp_filter(v, in, (fmt & kFmtPcmIn) != 0, stream_stride, sample_stride, slot, s)); break;
-        case 1: CK(launch_pitch(v, slot, s)); break;
+        case 1: CK(launch_pitch(v, slot, b->pitch_exact, s)); break;
         case 2: CK(launch_analysis(v, b->d_tab, slot, s)); break;
         case 3:
             if (b->rnn_fp32) CK(launch_rnn(v, b->um.dm, b->d_tab, s));
@@ -650,7 +653,11 @@ RNNoiseBatch* rnnoise_batch_create(const RNNModel* model, int n_streams, int dev
     RNNoiseBatch* b = new (std::nothrow) RNNoiseBatch();
     if (!b) return nullptr;
     const HostModel& hm = model ? model->m : HostModel::builtin();
-    if (batch_init(b, hm, n_streams, device) != 0) {
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);  // batch_init selects the batch's device; the caller's current device is restored below
+    const int rc = batch_init(b, hm, n_streams, device);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    if (rc != 0) {
         std::string keep = g_err;
         batch_release(b);
         delete b;
@@ -670,7 +677,7 @@ int rnnoise_batch_streams(const RNNoiseBatch* b) { return b ? b->n_streams : 0; 
 
 int rnnoise_batch_reset(RNNoiseBatch* b) {
     if (!b) return fail("null batch");
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     return zero_state(b);
 }
 
@@ -680,7 +687,7 @@ static int process_device_impl(RNNoiseBatch* b, void* out, const void* in, int f
     if (sample_stride < 1) return fail("sample_stride must be >= 1");
     if (n_frames < 0) return fail("negative n_frames");
     if (n_frames == 0) return 0;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     if (fmt < 0 || fmt > 3) return fail("pcm16 must be 0..3");
     const size_t esz_in = (fmt & kFmtPcmIn) ? sizeof(short) : sizeof(float), esz_out = (fmt & kFmtPcmOut) ? sizeof(short) : sizeof(float);
     auto at_in = [&](const void* p, int t) { return (const void*)((const char*)p + (size_t)t * frame_stride * esz_in); };
@@ -735,7 +742,7 @@ int rnnoise_batch_profile_step(RNNoiseBatch* b, float* out, const float* in, flo
                                float* ms, int cap) {
     if (!b || !out || !in || !ms) return fail("null argument");
     if (cap < kNumKernels) return fail("ms[] too small");
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     if (sync_all(b)) return -1;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->st[0];
     cudaEvent_t ev[kNumKernels + 1];
@@ -758,30 +765,42 @@ int rnnoise_batch_profile_step(RNNoiseBatch* b, float* out, const float* in, flo
 }
 
 // Host buffers: frame t is copied in on c_in, processed on the stage streams, copied out on c_out; copies of
-// neighbouring frames overlap the kernels (true overlap needs page-locked host memory).  16-bit PCM is consumed
-// and produced by the kernels directly (half the bytes over PCIe and HBM).
+// neighbouring frames overlap the kernels (true overlap needs page-locked host memory).  The device staging is a ring
+// of kStageSlots frames whatever the length of the call: slot k is refilled as soon as the high-pass kernel of the
+// frame that used it has consumed its input, and rewritten by the synthesis kernel as soon as that frame's D2H copy
+// has finished -- so the copy/compute pipeline depth does not depend on n_frames and a call of any length needs the
+// same memory.  16-bit PCM is consumed and produced by the kernels directly (half the bytes over PCIe and HBM).
 static int process_host_impl(RNNoiseBatch* b, void* out, const void* in, bool pcm, float* vad, int n_frames) {
-    if (ensure_stage(b, n_frames, pcm)) return -1;
+    if (ensure_stage(b, pcm)) return -1;
     const size_t B = (size_t)b->n_streams, fs = B * FRAME_SIZE;
     const size_t esz = pcm ? sizeof(short) : sizeof(float);
-    char* din = pcm ? (char*)b->stage_pcm_in : (char*)b->stage_in;
-    char* dout = pcm ? (char*)b->stage_pcm_out : (char*)b->stage_out;
+    char* din = b->stage_in;
+    char* dout = b->stage_out;
+    const int last = kNumKernels - 1;
     // everything issued earlier on the stage streams may still be reading/writing the staging buffers
     if (join_into(b, b->c_in)) return -1;
     for (int t = 0; t < n_frames; t++) {
-        const int e = (int)(b->frame % kEvRing);
-        CK(cudaMemcpyAsync(din + t * fs * esz, (const char*)in + t * fs * esz, fs * esz, cudaMemcpyHostToDevice, b->c_in));
+        const int e = (int)(b->frame % kEvRing), k = t % kStageSlots;
+        cudaStream_t first_st = b->st[0], last_st = b->serial ? b->st[0] : b->st[last];
+        if (t >= kStageSlots) {
+            // input slot: consumed by the first kernel of the frame that used it; output slot: drained by its D2H copy
+            CK(cudaStreamWaitEvent(b->c_in, b->serial ? b->ev[last][b->slot_ev[k]] : b->ev[0][b->slot_ev[k]], 0));
+            CK(cudaStreamWaitEvent(last_st, b->ev_out[k], 0));
+        }
+        CK(cudaMemcpyAsync(din + k * fs * esz, (const char*)in + (size_t)t * fs * esz, fs * esz, cudaMemcpyHostToDevice, b->c_in));
         CK(cudaEventRecord(b->ev_in[e], b->c_in));
         if (b->serial) {
-            CK(cudaStreamWaitEvent(b->st[0], b->ev_in[e], 0));
-            if (step_serial(b, dout + t * fs * esz, din + t * fs * esz, pcm ? kFmtPcm : kFmtF32, b->stage_vad + (size_t)t * B, FRAME_SIZE, 1, b->st[0])) return -1;
-            CK(cudaEventRecord(b->ev[kNumKernels - 1][e], b->st[0]));
+            CK(cudaStreamWaitEvent(first_st, b->ev_in[e], 0));
+            if (step_serial(b, dout + k * fs * esz, din + k * fs * esz, pcm ? kFmtPcm : kFmtF32, b->stage_vad + (size_t)k * B, FRAME_SIZE, 1, first_st)) return -1;
+            CK(cudaEventRecord(b->ev[last][e], first_st));
         } else {
-            if (step_pipelined(b, dout + t * fs * esz, din + t * fs * esz, pcm ? kFmtPcm : kFmtF32, b->stage_vad + (size_t)t * B, FRAME_SIZE, 1, b->ev_in[e])) return -1;
+            if (step_pipelined(b, dout + k * fs * esz, din + k * fs * esz, pcm ? kFmtPcm : kFmtF32, b->stage_vad + (size_t)k * B, FRAME_SIZE, 1, b->ev_in[e])) return -1;
         }
-        CK(cudaStreamWaitEvent(b->c_out, b->ev[kNumKernels - 1][e], 0));
-        CK(cudaMemcpyAsync((char*)out + t * fs * esz, dout + t * fs * esz, fs * esz, cudaMemcpyDeviceToHost, b->c_out));
-        if (vad) CK(cudaMemcpyAsync(vad + (size_t)t * B, b->stage_vad + (size_t)t * B, B * sizeof(float), cudaMemcpyDeviceToHost, b->c_out));
+        CK(cudaStreamWaitEvent(b->c_out, b->ev[last][e], 0));
+        CK(cudaMemcpyAsync((char*)out + (size_t)t * fs * esz, dout + k * fs * esz, fs * esz, cudaMemcpyDeviceToHost, b->c_out));
+        if (vad) CK(cudaMemcpyAsync(vad + (size_t)t * B, b->stage_vad + (size_t)k * B, B * sizeof(float), cudaMemcpyDeviceToHost, b->c_out));
+        CK(cudaEventRecord(b->ev_out[k], b->c_out));
+        b->slot_ev[k] = e;
     }
     CK(cudaStreamSynchronize(b->c_out));
     CK(cudaStreamSynchronize(b->c_in));
@@ -791,20 +810,28 @@ static int process_host_impl(RNNoiseBatch* b, void* out, const void* in, bool pc
 int rnnoise_batch_process_host(RNNoiseBatch* b, float* out, const float* in, float* vad, int n_frames) {
     if (!b || !out || !in) return fail("null argument");
     if (n_frames <= 0) return n_frames == 0 ? 0 : fail("negative n_frames");
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     return process_host_impl(b, out, in, false, vad, n_frames);
 }
 
 int rnnoise_batch_process_pcm16_host(RNNoiseBatch* b, short* out, const short* in, float* vad, int n_frames) {
     if (!b || !out || !in) return fail("null argument");
     if (n_frames <= 0) return n_frames == 0 ? 0 : fail("negative n_frames");
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     return process_host_impl(b, out, in, true, vad, n_frames);
+}
+
+int rnnoise_batch_pitch_stats(RNNoiseBatch* b, unsigned long long out[3]) {
+    if (!b || !out) return fail("null argument");
+    ON_DEVICE(b->device);
+    if (sync_all(b)) return -1;
+    CK(cudaMemcpy(out, b->buf.pitch_stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int rnnoise_batch_get_taps(RNNoiseBatch* b, int* pitch, int* silence, float* features, float* gains) {
     if (!b) return fail("null batch");
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     const size_t B = (size_t)b->n_streams;
     if (sync_all(b)) return -1;
     const BatchBuffers v = view(b, b->frame ? b->frame - 1 : 0);
@@ -834,10 +861,8 @@ namespace {
 
 void trainer_release(RNNoiseTrainer* t) {
     if (!t) return;
-    if (t->batch) {
-        cudaSetDevice(t->batch->device);
-        sync_all(t->batch);
-    }
+    DeviceGuard guard(t->batch ? t->batch->device : 0);
+    if (t->batch) sync_all(t->batch);
     cudaFree(t->tb.params);
     cudaFree(t->tb.resp_mem);
     cudaFree(t->tb.vad_count);
@@ -886,7 +911,7 @@ int train_step(RNNoiseTrainer* t, float* rows, long row_lane_stride, const float
         if (!s0 && i > 0) CK(cudaStreamWaitEvent(S(i), b->ev[i - 1][e], 0));
         switch (i) {
             case 0: CK(launch_train_front(v, t->tb, set, sig, noise, stream_stride, slot, S(i))); break;
-            case 1: CK(launch_pitch(v, slot, S(i))); break;
+            case 1: CK(launch_pitch(v, slot, b->pitch_exact, S(i))); break;
             case 2: CK(launch_analysis(v, b->d_tab, slot, S(i))); break;
             default: CK(launch_train_rows(v, t->tb, set, rows, row_lane_stride, S(i))); break;
         }
@@ -916,7 +941,12 @@ RNNoiseTrainer* rnnoise_train_create(int n_lanes, int device) {
     RNNoiseTrainer* t = new (std::nothrow) RNNoiseTrainer();
     if (!t) return nullptr;
     t->batch = rnnoise_batch_create(nullptr, 3 * n_lanes, device);
-    if (!t->batch || trainer_init(t, n_lanes) != 0) {
+    int trc = -1;
+    if (t->batch) {
+        DeviceGuard guard(t->batch->device);  // the trainer's own buffers live on the batch's device
+        trc = guard.err == cudaSuccess ? trainer_init(t, n_lanes) : fail("cudaSetDevice", guard.err);
+    }
+    if (!t->batch || trc != 0) {
         std::string keep = g_err;
         trainer_release(t);
         g_err = keep;
@@ -940,7 +970,7 @@ int rnnoise_train_set_params(RNNoiseTrainer* t, int first_lane, int n, const RNN
     if (first_lane < 0 || n < 0 || first_lane + n > t->tb.n_lanes) return fail("lane range out of bounds");
     for (int i = 0; i < n; i++)
         if (params[i].band_lp < 0 || params[i].band_lp >= NB_BANDS) return fail("band_lp must be in [0, 21]");
-    CK(cudaSetDevice(t->batch->device));
+    ON_DEVICE(t->batch->device);
     if (sync_all(t->batch)) return -1;  // frames in flight still read the old parameters
     CK(cudaMemcpy(t->tb.params + first_lane, params, (size_t)n * sizeof(TrainLaneParams), cudaMemcpyHostToDevice));
     return 0;
@@ -952,7 +982,7 @@ int rnnoise_train_process_device(RNNoiseTrainer* t, float* rows, const float* si
     if (n_frames < 0) return fail("negative n_frames");
     if (n_frames == 0) return 0;
     RNNoiseBatch* b = t->batch;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     cudaStream_t us = (cudaStream_t)cuda_stream;
     cudaEvent_t ready = nullptr;
     if (us) {
@@ -977,7 +1007,7 @@ int rnnoise_train_process_host(RNNoiseTrainer* t, float* rows, const float* sign
     if (n_frames < 0) return fail("negative n_frames");
     if (n_frames == 0) return 0;
     RNNoiseBatch* b = t->batch;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     const size_t L = (size_t)t->tb.n_lanes;
     // staging is bounded (<= 256 MiB per input buffer): long runs go through in chunks of frames
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_frames, (size_t(256) << 20) / (L * FRAME_SIZE * sizeof(float))));

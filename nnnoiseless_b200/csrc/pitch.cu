@@ -1,25 +1,42 @@
-// pitch.cu -- ORDER-EXACT pitch analysis (src/pitch.rs:45-489), 16 streams per thread block.
+// pitch.cu -- pitch analysis (src/pitch.rs:45-489) with a BIT-IDENTICAL integer period, 16 streams per block.
 //
-// Compiled with -fmad=false and written with explicit round-to-nearest intrinsics: every f32 operation
-// is rounded like the reference's scalar code and every sum runs in the reference's order, so the pitch
-// period (an integer) is bit-identical to the reference restatement for every frame.
+// Compiled with -fmad=false; every operation whose value reaches an output or the carried state is written
+// with explicit round-to-nearest intrinsics in the reference's order (same roundings, same summation order).
 //
-// Why many streams per block: the pitch path alternates strictly sequential recurrences (5-lag
-// autocorrelation sums, Levinson, running energies with a clamp per step, best/second-best selection,
-// the k = 2..15 sub-harmonic ladder) with small dense sums (147-lag cross-correlation, ~40 inner
-// products of 480).  With one stream per block the recurrences run on one lane of a warp (measured:
-// 18.6 of 32 lanes active, 25.7k warp-instructions per stream).  Here every recurrence runs
-// LANE-PER-STREAM (the block's streams advance in lock-step in one warp, operands fetched as float4 rows of the
-// shared-memory tile), while the dense sums are spread over (stream, lag-group) lane-tasks packed
-// densely into warps and use register sliding windows (one LDS.128 per 16 multiply-adds).
+// Two families of dot products dominate the path: the 147-lag coarse cross-correlation (src/pitch.rs:82,
+// 296-363: 35k multiply-adds per stream-frame) and the sub-harmonic inner products of remove_doubling
+// (src/pitch.rs:152-168: up to 23 x 480).  Neither value is an output: they only feed COMPARISONS
+// (find_best_pitch's selection, the g1 > thresh ladder).  They are therefore computed with FMA in whatever
+// order maps best onto the machine, and every comparison is certified:
+//   for ANY order and any mix of fused / unfused roundings  |computed - exact| <= gamma_n sum|x_j y_j|
+//   <= gamma_n ||x|| ||y||  (gamma_n = n u / (1 - n u), u = 2^-24), so a fast value and the reference's value
+//   differ by at most kappa ||x|| ||y||, kappa = 2 gamma_n.
+//   * coarse search: scores r_i = c_i^2 / y_i with intervals [lo_i, hi_i]; candidate set C = {j : hi_j (1+eta) >=
+//     min(lo_F1, lo_F2)} around the approximate top two.  |C| = 2 with lo_F1 > hi_F2 (1+eta): (best, second) =
+//     (F1, F2).  Otherwise the <= 8 candidates are recomputed in the reference's order, each must beat every
+//     non-candidate's upper bound robustly, and the reference's sequential selection runs on C alone.  (If a set
+//     "top" of >= 2 lags robustly beats every other lag, find_best_pitch ends in the same state as its scan
+//     restricted to top: DESIGN.md section 4.)  Anything else: all 147 lags of that stream are recomputed exactly.
+//   * remove_doubling: |g1^ - thresh^| > dg1 + 0.9 dg0 + 1e-6, else all inner products of that stream are
+//     recomputed exactly and the ladder is replayed on them.
+// What becomes STATE or OUTPUT (last_gain, the +-1 refinements, the fine search) is always order-exact.
+// tools/pitch_fast_model.c is the CPU model of this logic (2.4M frames against the oracle: 0 mismatches, 0.56 % of
+// stream-frames need an exact recomputation); tests/test_gpu_parity.py::test_pitch_mass_* is the GPU check.
 //
-// Shared-memory tile (dynamic, SB = 16 streams per block -> ~105 KB, two blocks per SM so that one block's
-// shared-memory-bound inner products overlap the other's FP-bound cross-correlation and serial phases):
+// Why many streams per block: the path alternates strictly sequential recurrences (5-lag autocorrelation,
+// Levinson, running energies with a clamp per step, the k = 2..15 ladder) with dense sums.  Recurrences run
+// LANE-PER-STREAM (operands fetched as float4 rows of the shared-memory tile); dense sums are spread over
+// (stream, lag-group) lane-tasks with register sliding windows, or one warp per stream with the 480 samples
+// dealt to the lanes (15 each: conflict-free scalar reads for arbitrary lags, x held in registers).
+//
+// Shared-memory tile (dynamic, SB = 16 streams per block -> ~111 KB, two blocks per SM):
 //   P   [SB][868]  2x-decimated, LPC-whitened history (pitch_buf); row stride 868 = 16B aligned and
 //                  = 4 (mod 32) so that lane-per-stream float4 reads are bank-conflict free
 //   Y4  [SB][436]  its even samples (the 4x-decimated signal); later reused for yy_lookup [SB][387]
-//   XC  [SB][149]  coarse cross-correlation      YN4 [SB][149]  coarse running energy
+//   XC  [SB][149]  coarse cross-correlation      YN4 [SB][149]  coarse running energy (exact)
 //   CK  [SB][39]   fine running energy, one checkpoint every 8 lags (replayed where the fine search needs it)
+#include <atomic>
+
 #include "common.cuh"
 
 namespace nnb {
@@ -29,6 +46,7 @@ namespace {
 __device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
 #ifndef PITCH_SB
 #define PITCH_SB 16
@@ -39,8 +57,7 @@ __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); 
 constexpr int SB = PITCH_SB;    // streams per block (lane-per-stream phases use lanes 0..SB-1, mirrored on the others)
 constexpr int NT = PITCH_NT;    // threads per block
 constexpr int NW = NT / 32;
-constexpr int BLOCKS_PER_SM = (227 * 1024) / ((SB * (868 + 436 + 2 * 149 + 31 + 11 + 29 + 39) + 64 * SB + 64) * 4 + 1024);
-static_assert(SB <= 32 && (32 % SB) == 0 && NW >= 4, "phase-to-warp assignment below assumes >= 4 warps");
+static_assert(SB == 16 && NW >= 4, "phase-to-warp assignment below assumes 16 streams and >= 4 warps");
 constexpr int PB = PITCH_BUF_SIZE / 2;                                 // 864
 constexpr int MAXP = PITCH_MAX_PERIOD - 3 * PITCH_MIN_PERIOD;          // 588
 constexpr int N4 = PITCH_FRAME_SIZE / 4;                               // 240
@@ -57,27 +74,47 @@ constexpr int YY_LD = 387;
 constexpr int IPR_LD = 31;
 constexpr int FX_LD = 11;
 constexpr int NGRP = (NL4 + 3) / 4;  // 37 lag groups of 4
+constexpr int CMAX = 8;              // coarse candidates recomputed exactly per stream
+constexpr int LAG_LD = 24;           // remove_doubling lags per stream: 1 + 2 * 11 (k <= 12 because t1 >= 30, t0 <= 383)
+constexpr int NSLOT = (NL4 + 31) / 32;  // 5 coarse lags per lane in the selection
+
+// 2 gamma_n with head-room: n = 240 (+ the final adds) and n = 480
+constexpr float KAPPA4 = 3.1e-5f;
+constexpr float KAPPA2 = 6.0e-5f;
+constexpr float ETA1 = 1.00001f;     // slack of every certified comparison (covers the float roundings of the check itself)
 
 constexpr int OFF_P = 0;
 constexpr int OFF_Y4 = OFF_P + SB * P_LD;
 constexpr int OFF_XC = OFF_Y4 + SB * Y4_LD;
 constexpr int OFF_YN4 = OFF_XC + SB * XC_LD;
-constexpr int OFF_AC = OFF_YN4 + SB * XC_LD;     // [5][32]
-constexpr int OFF_LPC = OFF_AC + 5 * SB;         // [5][32]
-constexpr int OFF_XX = OFF_LPC + 5 * SB;         // [32]
-constexpr int OFF_PG = OFF_XX + SB;              // [32]
-constexpr int OFF_IPR = OFF_PG + SB;             // [SB][31]
+constexpr int OFF_AC = OFF_YN4 + SB * XC_LD;     // [5][SB]
+constexpr int OFF_LPC = OFF_AC + 5 * SB;         // [5][SB]
+constexpr int OFF_XX = OFF_LPC + 5 * SB;         // [SB]
+constexpr int OFF_BND = OFF_XX + SB;             // [3][SB]: sum x_lp4^2 | sum P[0..384)^2 | sum Y4[0..192)^2
+constexpr int OFF_IPR = OFF_BND + 3 * SB;        // [SB][31]
 constexpr int OFF_FX = OFF_IPR + SB * IPR_LD;    // [SB][11]
-constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [4][SB]: best4, second4, t0, t; then 4 counters
-constexpr int OFF_TASK = OFF_SI + 4 * SB + 4;    // int [SB*29]: compacted remove_doubling inner-product tasks
+constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [5][SB]: best4, second4, t0, t, t1b
+constexpr int OFF_CTR = OFF_SI + 5 * SB;         // int [8]
+constexpr int OFF_LAGS = OFF_CTR + 8;            // int [SB][24]
+constexpr int OFF_NLAG = OFF_LAGS + SB * LAG_LD; // int [SB]
+constexpr int OFF_FLAG = OFF_NLAG + SB;          // int [SB]: bit 0 coarse all-exact, bit 1 remove_doubling all-exact, bit 2 coarse resolved
+constexpr int OFF_CXL = OFF_FLAG + SB;           // int [SB]: streams whose coarse search is recomputed exactly
+constexpr int OFF_RXL = OFF_CXL + SB;            // int [SB]: streams whose ladder is recomputed exactly
 constexpr int CK_STEP = 8;                         // fine running energy: one checkpoint every 8 lags
 constexpr int CK_N = (NL2 + CK_STEP - 1) / CK_STEP;  // 37
 constexpr int CK_LD = 39;
-constexpr int OFF_CK = OFF_TASK + SB * 29;          // [SB][39]
+constexpr int OFF_CK = OFF_RXL + SB;               // [SB][39]
 constexpr int SMEM_FLOATS = OFF_CK + SB * CK_LD;
+// scratch of the coarse selection, alive only before FX / IPR are first written: aliased onto them
+constexpr int OFF_CAND = OFF_IPR;                  // int [SB][CMAX]
+constexpr int OFF_CEX = OFF_CAND + SB * CMAX;      // [SB][CMAX]
+constexpr int OFF_XT = OFF_CEX + SB * CMAX;        // int [SB * CMAX]
+constexpr int OFF_MB = OFF_XT + SB * CMAX;         // [2][SB]
+constexpr int OFF_NEEDX = OFF_MB + 2 * SB;         // int [SB]
+static_assert(OFF_NEEDX + SB <= OFF_SI, "selection scratch must fit in the IPR + FX region");
 static_assert(CK_N <= CK_LD, "checkpoint row too short");
 static_assert(YY_LD <= Y4_LD, "yy must fit in the Y4 region");
-static_assert(SMEM_FLOATS * 4 + 1024 <= 227 * 1024, "tile must fit in one SM");
+static_assert(2 * (SMEM_FLOATS * 4 + 1024) <= 228 * 1024, "two blocks per SM");
 
 
 __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
@@ -140,8 +177,8 @@ __device__ __forceinline__ float inner_prod_480(const float4* __restrict__ xr, c
     return fa(fa(fa(s0, s1), s2), s3);
 }
 
-// Five consecutive lags lag0..lag0+4 of inner_prod(x, y + lag, 480) for one stream with ONE sliding register
-// window over y: acc[c][u] is the reference's accumulator u of lag c (src/pitch.rs:225-244), y read once.
+// NLAG consecutive lags of inner_prod(x, y + lag, 480) for one stream with ONE sliding register window over y:
+// acc[c][u] is the reference's accumulator u of lag c (src/pitch.rs:225-244), y read once.
 template <int NLAG>
 __device__ __forceinline__ void inner_prod_window(const float4* __restrict__ xr, const float* __restrict__ y, float* out) {
     float acc[NLAG][4];
@@ -169,6 +206,44 @@ __device__ __forceinline__ void inner_prod_window(const float4* __restrict__ xr,
     for (int c = 0; c < NLAG; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
 }
 
+// Four consecutive coarse lags 4g..4g+3 of one stream (src/pitch.rs:82, 296-363): every accumulator sums
+// x_lp4[j] * y_lp4[lag + j] with j ascending, operands via a sliding register window (one LDS.128 per 16 MACs).
+// EXACT: separate multiply and add in the reference's order.  !EXACT: fused, certified afterwards.
+template <bool EXACT>
+__device__ __forceinline__ void coarse_group(const float* __restrict__ y4row, int g, float* __restrict__ xcrow) {
+    const float4* xr = reinterpret_cast<const float4*>(y4row + HALF_MAX / 2);
+    const float4* yr = reinterpret_cast<const float4*>(y4row + 4 * g);
+    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+    float4 w = yr[0];
+#pragma unroll 2
+    for (int m = 0; m < N4 / 4; m++) {
+        const float4 x = xr[m];
+        const float4 wn = yr[m + 1];
+        const float e[8] = {w.x, w.y, w.z, w.w, wn.x, wn.y, wn.z, wn.w};
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (EXACT) {
+                c0 = fa(c0, fm(xv[u], e[u]));
+                c1 = fa(c1, fm(xv[u], e[u + 1]));
+                c2 = fa(c2, fm(xv[u], e[u + 2]));
+                c3 = fa(c3, fm(xv[u], e[u + 3]));
+            } else {
+                c0 = ffma(xv[u], e[u], c0);
+                c1 = ffma(xv[u], e[u + 1], c1);
+                c2 = ffma(xv[u], e[u + 2], c2);
+                c3 = ffma(xv[u], e[u + 3], c3);
+            }
+        }
+        w = wn;
+    }
+    float* o = xcrow + 4 * g;
+    o[0] = c0;
+    o[1] = c1;
+    o[2] = c2;
+    if (4 * g + 3 < NL4) o[3] = c3;
+}
+
 #ifdef PITCH_PROFILE
 __device__ unsigned long long g_pitch_prof[16];
 #define PPROF(k)                                                                  \
@@ -183,9 +258,12 @@ __device__ unsigned long long g_pitch_prof[16];
 #define PPROF(k)
 #endif
 
-__global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_SM : 512 / NT) pitch_kernel(const float* __restrict__ hist, int32_t* __restrict__ last_period,
+// stats[0] += streams whose coarse search was recomputed exactly, stats[1] += streams whose ladder was,
+// stats[2] += streams processed (one atomic per block each)
+__global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ hist, int32_t* __restrict__ last_period,
                                                       float* __restrict__ last_gain, int32_t* __restrict__ pitch_out,
-                                                      int n_streams, int hbase) {
+                                                      int n_streams, int hbase, int force_exact,
+                                                      unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) float sm[];
     float* P = sm + OFF_P;
     float* Y4 = sm + OFF_Y4;
@@ -194,12 +272,24 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
     float* AC = sm + OFF_AC;
     float* LPC = sm + OFF_LPC;
     float* XX = sm + OFF_XX;
+    float* BND = sm + OFF_BND;
     float* IPR = sm + OFF_IPR;
     float* FX = sm + OFF_FX;
     int* SI = reinterpret_cast<int*>(sm + OFF_SI);
-    int* CTR = SI + 4 * SB;  // [0] xcorr task counter, [1] rd task counter, [2] number of rd tasks
-    int* TASK = reinterpret_cast<int*>(sm + OFF_TASK);
+    int* CTR = reinterpret_cast<int*>(sm + OFF_CTR);
+    // CTR: [0] coarse lane-task counter, [1] remove_doubling stream counter, [2] streams in CXL, [3] entries in XT,
+    //      [4] streams in RXL, [7] CXL entries already recomputed
+    int* LAGS = reinterpret_cast<int*>(sm + OFF_LAGS);
+    int* NLAG = reinterpret_cast<int*>(sm + OFF_NLAG);
+    int* FLAG = reinterpret_cast<int*>(sm + OFF_FLAG);
+    int* CXL = reinterpret_cast<int*>(sm + OFF_CXL);
+    int* RXL = reinterpret_cast<int*>(sm + OFF_RXL);
     float* CK = sm + OFF_CK;
+    int* CAND = reinterpret_cast<int*>(sm + OFF_CAND);
+    float* CEX = sm + OFF_CEX;
+    int* XT = reinterpret_cast<int*>(sm + OFF_XT);
+    float* MB = sm + OFF_MB;
+    int* NEEDX = reinterpret_cast<int*>(sm + OFF_NEEDX);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ls = lane % SB;  // lane-per-stream phases: lanes >= SB mirror lanes < SB (same reads, same writes)
@@ -252,7 +342,8 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
             Y4[r * Y4_LD + PB / 2 + lane] = 0.0f;
         }
     }
-    if (tid < 4) CTR[tid] = 0;
+    if (tid < 8) CTR[tid] = 0;
+    if (tid < SB) FLAG[tid] = 0;
     __syncthreads();
     PPROF(0);
 
@@ -355,7 +446,7 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
     __syncthreads();
     PPROF(3);
 
-    // ---- Ph5: coarse running energy (warp NW-2) + xx (warp NW-1), then coarse xcorr on all warps ----
+    // ---- Ph5: serial chains on three warps, then the coarse cross-correlation (FMA) on all warps ----
     if (warp == NW - 2) {
         // y_sq_norm of find_best_pitch(xcorr, y_lp4, 240) (src/pitch.rs:379-382, 401-402); YN4[i] = value seen at lag i
         const float4* row = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD);
@@ -406,21 +497,48 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
             if ((m & 1) == 1) ck[(m + 1) >> 1] = y;  // after 4 (m + 1) steps
         }
     } else if (warp == NW - 1) {
-        // xx = inner_prod(x, x, 480) with its four interleaved accumulators (src/pitch.rs:133, 225-244)
-        const float4* xr = reinterpret_cast<const float4*>(P + ls * P_LD + HALF_MAX);
+        // Four energies, one code path for both half-warps (h = lane >> 4):
+        //   h = 0: xx = inner_prod(x, x, 480) with its four interleaved accumulators (src/pitch.rs:133, 225-244: EXACT,
+        //          it reaches last_gain), then sum x_lp4^2 = Y4[192..432)
+        //   h = 1: sum P[0..384)^2, then sum Y4[0..192)^2          (the last three only bound rounding errors)
+        const int h = lane >> 4;
+        const float4* pr = reinterpret_cast<const float4*>(P + ls * P_LD) + (h ? 0 : HALF_MAX / 4);
+        const int np = h ? HALF_MAX / 4 : HALF_N / 4;
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll 4
         for (int m = 0; m < HALF_N / 4; m++) {
-            const float4 x = xr[m];
-            a0 = fa(a0, fm(x.x, x.x));
-            a1 = fa(a1, fm(x.y, x.y));
-            a2 = fa(a2, fm(x.z, x.z));
-            a3 = fa(a3, fm(x.w, x.w));
+            if (m < np) {
+                const float4 x = pr[m];
+                a0 = fa(a0, fm(x.x, x.x));
+                a1 = fa(a1, fm(x.y, x.y));
+                a2 = fa(a2, fm(x.z, x.z));
+                a3 = fa(a3, fm(x.w, x.w));
+            }
         }
-        XX[ls] = fa(fa(fa(a0, a1), a2), a3);
+        const float sp = fa(fa(fa(a0, a1), a2), a3);
+        const float4* yr = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD) + (h ? 0 : HALF_MAX / 8);
+        const int ny = h ? HALF_MAX / 8 : N4 / 4;
+        a0 = a1 = a2 = a3 = 0.0f;
+#pragma unroll 4
+        for (int m = 0; m < N4 / 4; m++) {
+            if (m < ny) {
+                const float4 x = yr[m];
+                a0 = fa(a0, fm(x.x, x.x));
+                a1 = fa(a1, fm(x.y, x.y));
+                a2 = fa(a2, fm(x.z, x.z));
+                a3 = fa(a3, fm(x.w, x.w));
+            }
+        }
+        const float sy = fa(fa(fa(a0, a1), a2), a3);
+        if (h == 0) {
+            XX[ls] = sp;
+            BND[0 * SB + ls] = sy;
+        } else {
+            BND[1 * SB + ls] = sp;
+            BND[2 * SB + ls] = sy;
+        }
     }
-    // coarse xcorr (src/pitch.rs:82, 296-363): lane-task = (stream, group of 4 consecutive lags); every
-    // accumulator sums x_lp4[j] * y_lp4[lag + j] with j ascending, operands via a sliding register window.
+    // coarse xcorr, FMA: lane-task = (stream, group of 4 consecutive lags)
     for (;;) {
         int T = 0;
         if (lane == 0) T = atomicAdd(&CTR[0], 1);
@@ -429,47 +547,209 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         const int L = T * 32 + lane;
         if (L < SB * NGRP) {
             const int s = L / NGRP, g = L - s * NGRP;
-            const float4* xr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + HALF_MAX / 2);
-            const float4* yr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + 4 * g);
-            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
-            float4 w = yr[0];
-#pragma unroll 2
-            for (int m = 0; m < N4 / 4; m++) {
-                const float4 x = xr[m];
-                const float4 wn = yr[m + 1];
-                const float e[8] = {w.x, w.y, w.z, w.w, wn.x, wn.y, wn.z, wn.w};
-                const float xv[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    c0 = fa(c0, fm(xv[u], e[u]));
-                    c1 = fa(c1, fm(xv[u], e[u + 1]));
-                    c2 = fa(c2, fm(xv[u], e[u + 2]));
-                    c3 = fa(c3, fm(xv[u], e[u + 3]));
-                }
-                w = wn;
-            }
-            float* o = XC + s * XC_LD + 4 * g;
-            o[0] = c0;
-            o[1] = c1;
-            o[2] = c2;
-            if (4 * g + 3 < NL4) o[3] = c3;
+            coarse_group<false>(Y4 + s * Y4_LD, g, XC + s * XC_LD);
         }
     }
     __syncthreads();
     PPROF(4);
 
-    // ---- Ph6a: warp 0: coarse best/second (serial over lags, lane = stream; src/pitch.rs:83-84) ----
-    if (warp == 0) {
-        BestTwo b2;
-        const float* xc = XC + ls * XC_LD;
-        const float* yn = YN4 + ls * XC_LD;
-#pragma unroll 7
-        for (int i = 0; i < NL4; i++) b2.consider(i, xc[i], yn[i]);
-        SI[0 * SB + ls] = b2.best;
-        SI[1 * SB + ls] = b2.second;
+    // ---- Ph6a: certified coarse selection, one warp per stream, lane = lags lane, lane + 32, ... (src/pitch.rs:83-84) ----
+    for (int s = warp; s < SB; s += NW) {
+        const float* xc = XC + s * XC_LD;
+        const float* yn = YN4 + s * XC_LD;
+        float cv[NSLOT], yv[NSLOT];
+#pragma unroll
+        for (int k = 0; k < NSLOT; k++) {
+            const int lag = lane + 32 * k;
+            cv[k] = lag < NL4 ? xc[lag] : 0.0f;
+            yv[k] = lag < NL4 ? yn[lag] : 1.0f;
+        }
+        // approximate top two by score c^2 / y (c > 0); "none" = (0, 1, -1)
+        float n1 = 0.0f, d1 = 1.0f, n2 = 0.0f, d2 = 1.0f;
+        int i1 = -1, i2 = -1;
+#pragma unroll
+        for (int k = 0; k < NSLOT; k++) {
+            const float num = cv[k] > 0.0f ? cv[k] * cv[k] : 0.0f;
+            const bool b1 = num * d1 > n1 * yv[k];
+            const bool b2 = num * d2 > n2 * yv[k];
+            if (b1) {
+                n2 = n1; d2 = d1; i2 = i1;
+                n1 = num; d1 = yv[k]; i1 = lane + 32 * k;
+            } else if (b2) {
+                n2 = num; d2 = yv[k]; i2 = lane + 32 * k;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float on1 = __shfl_xor_sync(0xffffffffu, n1, off), od1 = __shfl_xor_sync(0xffffffffu, d1, off);
+            const float on2 = __shfl_xor_sync(0xffffffffu, n2, off), od2 = __shfl_xor_sync(0xffffffffu, d2, off);
+            const int oi1 = __shfl_xor_sync(0xffffffffu, i1, off), oi2 = __shfl_xor_sync(0xffffffffu, i2, off);
+            if (on1 * d1 > n1 * od1) {            // the other side's best wins: second = max(my best, its second)
+                const bool c = on2 * d1 > n1 * od2;
+                n2 = c ? on2 : n1; d2 = c ? od2 : d1; i2 = c ? oi2 : i1;
+                n1 = on1; d1 = od1; i1 = oi1;
+            } else {                               // my best stays: second = max(my second, its best)
+                const bool c = on1 * d2 > n2 * od1;
+                n2 = c ? on1 : n2; d2 = c ? od1 : d2; i2 = c ? oi1 : i2;
+            }
+        }
+        const int f1 = __shfl_sync(0xffffffffu, i1, 0), f2 = __shfl_sync(0xffffffffu, i2, 0);
+        const float ex4 = BND[0 * SB + s], y4tot = BND[2 * SB + s] + ex4;
+        const float delta = KAPPA4 * sqrtf(ex4 * y4tot) * 1.001f;
+        int best = 0, second = 1, nc = 0;
+        bool cx = force_exact != 0, need = false;
+        if (!(delta < 1e30f)) {
+            cx = true;  // inf / nan
+        } else if (f1 < 0) {
+            if (delta != 0.0f) cx = true;  // else every c_i is exactly 0: the reference keeps its initial (0, 1)
+        } else if (f2 < 0 || f2 == f1) {
+            cx = true;
+        } else {
+            const float c1 = xc[f1], c2 = xc[f2], y1 = yn[f1], y2 = yn[f2];
+            const float a1 = c1 - delta, a2 = c2 - delta;
+            if (!(a1 > 0.0f) || !(a2 > 0.0f) || !(a2 * a2 > 1e-20f) || !(c1 < 1e18f)) {
+                cx = true;
+            } else {
+                float tn = a1 * a1, td = y1;  // T0 = min(lo_F1, lo_F2) as a fraction
+                if (a2 * a2 * td < tn * y2) {
+                    tn = a2 * a2;
+                    td = y2;
+                }
+                unsigned inmask = 0, masks[NSLOT];
+                float mn = 0.0f, md = 1.0f;  // M = max upper bound over the non-candidates
+#pragma unroll
+                for (int k = 0; k < NSLOT; k++) {
+                    const int lag = lane + 32 * k;
+                    const float b = fmaxf(cv[k] + delta, 0.0f);
+                    const float hn = b * b;
+                    const bool in_c = lag < NL4 && ((lag == f1 || lag == f2) || (hn * td * ETA1 >= tn * yv[k]));
+                    masks[k] = __ballot_sync(0xffffffffu, in_c);
+                    if (in_c) inmask |= 1u << k;
+                    if (lag < NL4 && !in_c && hn * md > mn * yv[k]) {
+                        mn = hn;
+                        md = yv[k];
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float omn = __shfl_xor_sync(0xffffffffu, mn, off), omd = __shfl_xor_sync(0xffffffffu, md, off);
+                    if (omn * md > mn * omd) {
+                        mn = omn;
+                        md = omd;
+                    }
+                }
+                mn = __shfl_sync(0xffffffffu, mn, 0);
+                md = __shfl_sync(0xffffffffu, md, 0);
+#pragma unroll
+                for (int k = 0; k < NSLOT; k++) nc += __popc(masks[k]);
+                if (nc > CMAX) {
+                    cx = true;
+                } else {
+                    int basek = 0;  // candidates in ascending lag order: slot-major, lane-minor
+#pragma unroll
+                    for (int k = 0; k < NSLOT; k++) {
+                        if ((inmask >> k) & 1u) CAND[s * CMAX + basek + __popc(masks[k] & ((1u << lane) - 1u))] = lane + 32 * k;
+                        basek += __popc(masks[k]);
+                    }
+                    const float b2 = c2 + delta;
+                    if (nc == 2 && a1 * a1 * y2 > b2 * b2 * y1 * ETA1) {
+                        best = f1;
+                        second = f2;
+                    } else {
+                        need = true;
+                    }
+                    if (lane == 0) {
+                        MB[s] = mn;
+                        MB[SB + s] = md;
+                    }
+                }
+            }
+        }
+        if (cx) need = false;
+        if (lane == 0) {
+            SI[0 * SB + s] = best;
+            SI[1 * SB + s] = second;
+            NEEDX[s] = need ? nc : 0;
+            if (cx) {
+                FLAG[s] = 1;
+                CXL[atomicAdd(&CTR[2], 1)] = s;
+            } else if (need) {
+                const int base = atomicAdd(&CTR[3], nc);
+                for (int i = 0; i < nc; i++) XT[base + i] = (s << 8) | i;
+            }
+        }
     }
     __syncthreads();
     PPROF(5);
+
+    // ---- Ph6x: exact recomputation where the certificate failed.  Round 0: the candidates of the "need" streams and all
+    // 147 lags of the CXL streams; round 1: all lags of streams whose candidates turned out not to dominate. ----
+    for (int round = 0; round < 2; round++) {
+        const int ncx_lo = CTR[7], ncx = CTR[2], nx = round == 0 ? CTR[3] : 0;
+        if (ncx == ncx_lo && nx == 0) break;  // block-uniform
+        for (int L = tid; L < nx; L += NT) {
+            const int e = XT[L], s = e >> 8, pos = e & 255;
+            const int lag = CAND[s * CMAX + pos];
+            const float4* xr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + HALF_MAX / 2);
+            const float* yr = Y4 + s * Y4_LD + lag;
+            float c = 0.0f;  // src/pitch.rs:296-363: one accumulator per lag, j ascending
+#pragma unroll 4
+            for (int m = 0; m < N4 / 4; m++) {
+                const float4 x = xr[m];
+                c = fa(c, fm(x.x, yr[4 * m]));
+                c = fa(c, fm(x.y, yr[4 * m + 1]));
+                c = fa(c, fm(x.z, yr[4 * m + 2]));
+                c = fa(c, fm(x.w, yr[4 * m + 3]));
+            }
+            CEX[s * CMAX + pos] = c;
+        }
+        for (int L = tid; L < (ncx - ncx_lo) * 40; L += NT) {
+            const int i = L / 40, g = L - i * 40;
+            if (g < NGRP) {
+                const int s = CXL[ncx_lo + i];
+                coarse_group<true>(Y4 + s * Y4_LD, g, XC + s * XC_LD);
+            }
+        }
+        __syncthreads();
+        if (warp == 0 && lane < SB) {
+            const int s = lane;
+            const float* xc = XC + s * XC_LD;
+            const float* yn = YN4 + s * XC_LD;
+            const int fl = FLAG[s];
+            if ((fl & 1) && !(fl & 4)) {
+                // the reference's scan over all lags on exact values
+                BestTwo b2;
+#pragma unroll 7
+                for (int i = 0; i < NL4; i++) b2.consider(i, xc[i], yn[i]);
+                SI[0 * SB + s] = b2.best;
+                SI[1 * SB + s] = b2.second;
+                FLAG[s] = fl | 4;
+            } else if (round == 0 && NEEDX[s] > 0) {
+                const int nc = NEEDX[s];
+                const float mn = MB[s], md = MB[SB + s];
+                BestTwo b2;
+                bool ok = true;
+                for (int k = 0; k < nc; k++) {
+                    const int lag = CAND[s * CMAX + k];
+                    const float c = CEX[s * CMAX + k], ysq = yn[lag];
+                    // every candidate must beat the upper bound of every non-candidate robustly
+                    if (!(c > 0.0f) || !(c * c * md > mn * ysq * ETA1)) ok = false;
+                    b2.consider(lag, c, ysq);
+                }
+                if (ok) {
+                    SI[0 * SB + s] = b2.best;
+                    SI[1 * SB + s] = b2.second;
+                } else {
+                    FLAG[s] = fl | 1;
+                    CXL[atomicAdd(&CTR[2], 1)] = s;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) CTR[7] = ncx;
+        __syncthreads();
+    }
+    PPROF(6);
 
     // ---- Ph6b: the two 5-lag fine windows of every stream (src/pitch.rs:88-96), each split into a 3-lag and a
     // 2-lag sliding window so that two warps share the work.  lane-task = (stream, window): lags i0c .. i0c+4, i0c =
@@ -495,7 +775,7 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         }
     }
     __syncthreads();
-    PPROF(6);
+    PPROF(7);
 
     // ---- Ph8: fine best + pseudo-interpolation (src/pitch.rs:97-114), lane = stream ----
     if (warp == 0) {
@@ -545,42 +825,34 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
         }
         const int pitch_idx = PITCH_MAX_PERIOD - (2 * best - offset);  // src/pitch.rs:49,114
         const int t0 = min(pitch_idx / 2, HALF_MAX - 1);                // t0 of remove_doubling
-        SI[2 * SB + ls] = t0;
-        // Compact list of the inner products remove_doubling will need (src/pitch.rs:134,152-168): xy(t0), then
-        // for k = 2.. while t1 >= min_period: lags t1 and t1b.  Entry = stream << 16 | q << 10 | lag.
+        // The lags remove_doubling needs (src/pitch.rs:134,152-168): t0, then for k = 2.. while t1 >= min_period the
+        // pair (t1, t1b); IPR[stream][1 + position] = inner_prod(x, x - lag, 480).
         // (k is a compile-time constant in the unrolled loops below: the divisions by 2k become multiply-shifts)
-        int nk = 0;
-#pragma unroll
-        for (int k = 2; k <= 15; k++)
-            if (nk == k - 2 && (2 * t0 + k) / (2 * k) >= MIN_PERIOD2) nk++;
-        const int n = (lane < SB) ? 1 + 2 * nk : 0;
-        int incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        if (lane == 31) CTR[2] = incl;
         if (lane < SB) {
-            int* tk = TASK + (incl - n);
-            tk[0] = (lane << 16) | (1 << 10) | t0;
+            SI[2 * SB + ls] = t0;
+            int* lg = LAGS + ls * LAG_LD;
+            lg[0] = t0;
+            int nk = 0;
 #pragma unroll
-            for (int k = 2; k <= 15; k++) {
+            for (int k = 2; k <= 12; k++) {
                 constexpr int sc[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};  // SECOND_CHECK, src/pitch.rs:489
-                const int j = k - 2;
-                if (j < nk) {
-                    const int t1 = (2 * t0 + k) / (2 * k);
+                const int t1 = (2 * t0 + k) / (2 * k);
+                if (nk == k - 2 && t1 >= MIN_PERIOD2) {
                     const int t1b = (k == 2) ? ((t1 + t0 > HALF_MAX) ? t0 : t0 + t1) : (2 * sc[k] * t0 + k) / (2 * k);
-                    tk[1 + 2 * j] = (lane << 16) | ((2 + 2 * j) << 10) | t1;
-                    tk[2 + 2 * j] = (lane << 16) | ((3 + 2 * j) << 10) | t1b;
+                    lg[1 + 2 * nk] = t1;
+                    lg[2 + 2 * nk] = t1b;
+                    nk++;
                 }
             }
+            NLAG[ls] = 1 + 2 * nk;
         }
     }
     __syncthreads();
-    PPROF(7);
+    PPROF(8);
 
-    // ---- Ph9: yy_lookup chain (warp NW-1 first) + remove_doubling inner products on all warps ----
+    // ---- Ph9: yy_lookup chain (warp NW-1 first) + remove_doubling inner products, FMA, one WARP per stream:
+    // lane l owns samples 15 l .. 15 l + 14 of x (registers) and of every lagged window (scalar reads at stride 15:
+    // conflict-free for any lag); eight lags share one transposed shuffle reduction. ----
     float* YY = Y4;  // the 4x-decimated copy is dead from here on
     if (warp == NW - 1) {
         // yy_lookup (src/pitch.rs:135-142): stored clamped at 0, carried unclamped; i = 1..384 walks the rows downwards
@@ -600,55 +872,84 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
             }
         }
     }
-    // lane-task = one entry of the compacted list (stream, q, lag): IPR[stream][q] = inner_prod(x, x - lag, 480)
-    {
-        const int ntask = CTR[2];
-        for (;;) {
-            int T = 0;
-            if (lane == 0) T = atomicAdd(&CTR[1], 1);
-            T = __shfl_sync(0xffffffffu, T, 0);
-            if (T * 32 >= ntask) break;
-            const int L = T * 32 + lane;
-            if (L < ntask) {
-                const int e = TASK[L];
-                const int s = e >> 16, q = (e >> 10) & 63, lagq = e & 1023;
-                const float* prow = P + s * P_LD;
-                IPR[s * IPR_LD + q] = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - lagq);
+    for (;;) {
+        int s = 0;
+        if (lane == 0) s = atomicAdd(&CTR[1], 1);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s >= SB) break;
+        const float* pl = P + s * P_LD + HALF_MAX + 15 * lane;
+        float xr[15];
+#pragma unroll
+        for (int j = 0; j < 15; j++) xr[j] = pl[j];
+        const int n = NLAG[s];
+        const int* lg = LAGS + s * LAG_LD;
+        for (int base = 0; base < n; base += 8) {
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                acc[i] = 0.0f;
+                if (base + i < n) {  // warp-uniform
+                    const float* y = pl - lg[base + i];
+#pragma unroll
+                    for (int j = 0; j < 15; j++) acc[i] = ffma(xr[j], y[j], acc[i]);
+                }
             }
+            // transposed reduction: after the three exchange steps lane l holds, in acc[0], the sum over the lanes
+            // {l ^ 16, l ^ 8, l ^ 4 combinations} of lag index 4 b4 + 2 b3 + b2 (bk = bit k of l)
+            const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const float send = h8 ? acc[i] : acc[i + 2], keep = h8 ? acc[i + 2] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {
+                const float send = h4 ? acc[0] : acc[1], keep = h4 ? acc[1] : acc[0];
+                acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+            const int idx = base + (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+            if ((lane & 3) == 0 && idx < n) IPR[s * IPR_LD + 1 + idx] = acc[0];
         }
     }
     __syncthreads();
-    PPROF(8);
+    PPROF(9);
 
-    // ---- Ph10-12: the sub-harmonic ladder (src/pitch.rs:144-203), the +-1 refinement (205-218) and the result,
-    // lane = stream, no further block-level synchronisation ----
-    if (warp == 0) {
+    // ---- Ph10a: the sub-harmonic ladder (src/pitch.rs:144-203) on the fast inner products, every decision certified ----
+    // pass == 0: fast values with margins; pass == 1 (only for streams in RXL): the same code on exact values.
+    auto ladder = [&](bool exact, int& t_out, int& t1b_out, bool& uncertain) {
         const float* ipr = IPR + ls * IPR_LD;
         const float* yy = YY + ls * YY_LD;
         const int t0 = SI[2 * SB + ls];
         const float xx = XX[ls];
-        float xy = ipr[1];
-        float yyv = yy[t0];
+        const float dip = exact ? 0.0f : KAPPA2 * sqrtf(xx * (BND[1 * SB + ls] + xx)) * 1.001f;
+        uncertain = !(dip < 1e30f);
+        const float xy0 = ipr[1];
+        const float yy0 = yy[t0];
         int prev_period = 0;
         float lg = 0.0f;
         if (ls < ns) {
             prev_period = last_period[s0 + ls] / 2;
             lg = last_gain[s0 + ls];
         }
-        float best_xy = xy, best_yy = yyv;
-        const float g0 = pitch_gain(xy, xx, yyv);
-        float g = g0;
-        int t = t0;
+        const float g0 = pitch_gain(xy0, xx, yy0);
+        const float dg0 = __fdiv_rn(dip, __fsqrt_rn(fa(1.0f, fm(xx, yy0))));
+        int t = t0, t1bs = t0;
 #pragma unroll
-        for (int k = 2; k <= 15; k++) {
+        for (int k = 2; k <= 12; k++) {
             constexpr int sc[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};  // SECOND_CHECK, src/pitch.rs:489
             const int t1 = (2 * t0 + k) / (2 * k);
             if (t1 < MIN_PERIOD2) break;
             int t1b;
             if (k == 2) t1b = (t1 + t0 > HALF_MAX) ? t0 : t0 + t1;
             else t1b = (2 * sc[k] * t0 + k) / (2 * k);
-            xy = fm(fa(ipr[2 + 2 * (k - 2)], ipr[3 + 2 * (k - 2)]), 0.5f);
-            yyv = fm(fa(yy[t1], yy[t1b]), 0.5f);
+            const float xy = fm(fa(ipr[2 + 2 * (k - 2)], ipr[3 + 2 * (k - 2)]), 0.5f);
+            const float yyv = fm(fa(yy[t1], yy[t1b]), 0.5f);
             const float g1 = pitch_gain(xy, xx, yyv);
             const int d = abs(t1 - prev_period);
             float cont;
@@ -659,22 +960,82 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
             if (t1 < 3 * MIN_PERIOD2) thresh = fmaxf(fs(fm(0.85f, g0), cont), 0.4f);
             else if (t1 < 2 * MIN_PERIOD2) thresh = fmaxf(fs(fm(0.9f, g0), cont), 0.5f);  // dead branch, as in the reference
             else thresh = fmaxf(fs(fm(0.7f, g0), cont), 0.3f);
+            if (!exact) {
+                const float dg1 = __fdiv_rn(dip, __fsqrt_rn(fa(1.0f, fm(xx, yyv))));
+                if (!(fabsf(g1 - thresh) > dg1 + 0.9f * dg0 + 1e-6f)) uncertain = true;
+            }
             if (g1 > thresh) {
-                best_xy = xy;
-                best_yy = yyv;
                 t = t1;
-                g = g1;
+                t1bs = t1b;
             }
         }
+        t_out = t;
+        t1b_out = t1bs;
+    };
+    if (warp == 0) {
+        int t, t1b;
+        bool unc;
+        ladder(false, t, t1b, unc);
+        if (force_exact) unc = true;
+        if (lane < SB) {
+            SI[3 * SB + ls] = t;
+            SI[4 * SB + ls] = t1b;
+            if (unc) {
+                FLAG[ls] |= 2;
+                RXL[atomicAdd(&CTR[4], 1)] = ls;
+            }
+        }
+    }
+    __syncthreads();
+    PPROF(10);
+
+    // ---- Ph10x: exact inner products (src/pitch.rs:225-244) of the streams whose ladder could not be certified ----
+    {
+        const int nrx = CTR[4];
+        if (nrx > 0) {  // block-uniform
+            for (int L = tid; L < nrx * LAG_LD; L += NT) {
+                const int i = L / LAG_LD, q = L - i * LAG_LD;
+                const int s = RXL[i];
+                if (q < NLAG[s]) {
+                    const float* prow = P + s * P_LD;
+                    IPR[s * IPR_LD + 1 + q] =
+                        inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - LAGS[s * LAG_LD + q]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- Ph10b-12: exact replay where needed, then what reaches the state and the output, always order-exact: the +-1
+    // refinement (src/pitch.rs:205-218) and last_gain (:199-203).  Lanes 0-15 slide a 3-lag window over lags t+1, t, t-1
+    // of their stream; lanes 16-31 run the SAME code at lag t1b (the second inner product behind best_xy). ----
+    if (warp == 0) {
+        int t = SI[3 * SB + ls], t1b = SI[4 * SB + ls];
+        if (FLAG[ls] & 2) {
+            bool dummy;
+            ladder(true, t, t1b, dummy);
+        }
+        const int t0 = SI[2 * SB + ls];
+        const float* yy = YY + ls * YY_LD;
+        const float xx = XX[ls];
+        const bool hi = lane >= SB;
+        float xc3[3];
+        const float* prow = P + ls * P_LD;
+        inner_prod_window<3>(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (hi ? t1b : t + 1), xc3);
+        const float x_0 = xc3[2], x_1 = xc3[1], x_2 = xc3[0];  // lanes 0-15: window slot c <-> lag t + 1 - c
+        const float ipb = __shfl_down_sync(0xffffffffu, xc3[0], SB);  // lanes 16-31: slot 0 <-> lag t1b
+        float best_xy, best_yy;
+        if (t == t0) {  // no sub-harmonic accepted (an accepted t1 is always < t0)
+            best_xy = x_1;
+            best_yy = yy[t0];
+        } else {
+            best_xy = fm(fa(x_1, ipb), 0.5f);
+            best_yy = fm(fa(yy[t], yy[t1b]), 0.5f);
+        }
+        const float g = pitch_gain(best_xy, xx, best_yy);
         best_xy = fmaxf(best_xy, 0.0f);
         float pg = (best_yy <= best_xy) ? 1.0f : __fdiv_rn(best_xy, fa(best_yy, 1.0f));
         pg = fminf(pg, g);
-
-        // xcorr at lags t-1, t, t+1: one sliding window starting at lag t+1 (lowest address)
-        float xc3[3];
-        const float* prow = P + ls * P_LD;
-        inner_prod_window<3>(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (t + 1), xc3);
-        const float x_0 = xc3[2], x_1 = xc3[1], x_2 = xc3[0];  // window slot c <-> lag t + 1 - c
         int offset = 0;
         if (fs(x_2, x_0) > fm(0.7f, fs(x_1, x_0))) offset = 1;
         else if (fs(x_0, x_2) > fm(0.7f, fs(x_1, x_2))) offset = -1;
@@ -684,8 +1045,18 @@ __global__ void __launch_bounds__(NT, (BLOCKS_PER_SM * NT <= 512) ? BLOCKS_PER_S
             last_period[s0 + lane] = tf;
             last_gain[s0 + lane] = pg;
         }
+        if (stats && lane == 0) {
+            int n_cx = 0, n_rx = 0;
+            for (int i = 0; i < ns; i++) {
+                n_cx += FLAG[i] & 1;
+                n_rx += (FLAG[i] >> 1) & 1;
+            }
+            if (n_cx) atomicAdd(&stats[0], (unsigned long long)n_cx);
+            if (n_rx) atomicAdd(&stats[1], (unsigned long long)n_rx);
+            atomicAdd(&stats[2], (unsigned long long)ns);
+        }
     }
-    PPROF(9);
+    PPROF(11);
 }
 
 }  // namespace
@@ -701,19 +1072,20 @@ extern "C" void nnb_pitch_prof_read(unsigned long long* out16, int reset) {
 }
 #endif
 
-cudaError_t launch_pitch(const BatchBuffers& b, int slot, cudaStream_t st) {
-    static unsigned long long attr_devs = 0;  // bit d: attribute set on device d
+cudaError_t launch_pitch(const BatchBuffers& b, int slot, bool force_exact, cudaStream_t st) {
+    static std::atomic<unsigned long long> attr_devs{0};  // bit d: attribute set on device d
     const size_t smem = sizeof(float) * SMEM_FLOATS;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev >= 64 || !((attr_devs >> dev) & 1ull)) {
+    if (dev >= 64 || !((attr_devs.load(std::memory_order_acquire) >> dev) & 1ull)) {
         e = cudaFuncSetAttribute(pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (dev < 64) attr_devs |= 1ull << dev;
+        if (dev < 64) attr_devs.fetch_or(1ull << dev, std::memory_order_release);
     }
     const int grid = (b.n_streams + SB - 1) / SB;
-    pitch_kernel<<<grid, NT, smem, st>>>(b.hist, b.last_period, b.last_gain, b.pitch, b.n_streams, hist_base(slot));
+    pitch_kernel<<<grid, NT, smem, st>>>(b.hist, b.last_period, b.last_gain, b.pitch, b.n_streams, hist_base(slot), force_exact ? 1 : 0,
+                                         b.pitch_stats);
     return cudaGetLastError();
 }
 

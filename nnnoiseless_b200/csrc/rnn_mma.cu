@@ -11,6 +11,8 @@
 //     update h = z h + (1-z) h~ happens in the accumulator layout without a transpose.
 // Activations: src/util.rs:29-53 (table tanh, sigmoid = .5 + .5 tanh(x/2), relu) chosen per layer at run time.
 // GRU semantics: src/rnn.rs:292-327 (reset gate applied to the state BEFORE the recurrent product).
+#include <atomic>
+
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -57,9 +59,10 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
-// x = hi + lo with hi, lo in f16 (|x| is clamped to the f16 range: 65504)
+// x = hi + lo with hi, lo in f16.  No clamp: NaN stays NaN, and |x| > 65504 (only an unbounded ReLU layer of a custom
+// model can get there) becomes +-inf in hi and -+inf in lo, i.e. NaN in every product -- a loud failure instead of a
+// silently clamped activation.  The bundled models (tanh / sigmoid, |x| <= 1) and the 42 features are far inside the range.
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
-    x = fminf(fmaxf(x, -65504.0f), 65504.0f);
     hi = __float2half_rn(x);
     lo = __float2half_rn(x - __half2float(hi));
 }
@@ -420,14 +423,17 @@ __global__ void __launch_bounds__(NT, RNN_MINB) rnn_mma_kernel(BatchBuffers bb, 
 
 cudaError_t launch_rnn_mma(const BatchBuffers& b, const DeviceModelMma& m, const DeviceTables* tab, cudaStream_t st) {
     const size_t smem = (size_t)TS * m.kp * 2 * 2 + (size_t)TS * m.hs * 4 + 208 * 4;
-    static size_t attr_smem[64] = {0};
+    static std::atomic<size_t> attr_smem[64];  // zero-initialised; concurrent host threads may race to raise it (idempotent)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev >= 64 || smem > attr_smem[dev]) {
+    if (dev >= 64 || smem > attr_smem[dev].load(std::memory_order_acquire)) {
         e = cudaFuncSetAttribute(rnn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (dev < 64) attr_smem[dev] = smem;
+        if (dev < 64) {
+            size_t cur = attr_smem[dev].load(std::memory_order_relaxed);
+            while (cur < smem && !attr_smem[dev].compare_exchange_weak(cur, smem, std::memory_order_release)) {}
+        }
     }
     const int grid = (b.n_streams + TS - 1) / TS;
     rnn_mma_kernel<<<grid, NT, smem, st>>>(b, m, tab);

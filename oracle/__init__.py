@@ -83,6 +83,7 @@ def lib():
         L.nno_irfft960.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.nno_pitch_only.restype = C.c_int32
         L.nno_pitch_only.argtypes = [C.c_void_p, C.c_void_p]
+        L.nno_set_fft_mode.argtypes = [C.c_int]
         L.nno_tansig.restype = C.c_float
         L.nno_tansig.argtypes = [C.c_float]
         L.nno_sigmoid.restype = C.c_float
@@ -158,6 +159,11 @@ class State:
         if getattr(self, "_h", None):
             lib().nno_state_free(self._h)
             self._h = None
+
+
+def set_fft_mode(mode: int):
+    """0 = the pinned f32 Stockham FFT (default), 1 = f64 DFT sums rounded once, 2 = f32 Stockham with another radix order."""
+    lib().nno_set_fft_mode(int(mode))
 
 
 def rfft960(x):

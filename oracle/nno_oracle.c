@@ -140,9 +140,36 @@ static void stockham_pass(int r, int n, int s, const cpx *x, cpx *y) {
     }
 }
 
+/* FFT variant (test aid, nno_set_fft_mode): 0 = the f32 Stockham above with radices 4,4,5,3,2 (default, the pinned
+ * oracle); 1 = the transforms evaluated as plain DFT sums in f64 and rounded to f32 once; 2 = the same f32 Stockham
+ * with the radix order 2,3,5,4,4 (a second, equally valid f32 FFT with a different rounding pattern).  Used by
+ * tests/test_oracle_golden.py to show how much two correct FFTs may differ after signal -> digital silence -> signal. */
+static int g_fft_mode = 0;
+void nno_set_fft_mode(int mode) { g_fft_mode = mode; }
+
+static double g_w960_re[960], g_w960_im[960];
+static int g_w960_ready = 0;
+static void ensure_w960(void) {
+    if (g_w960_ready) return;
+#ifdef _OPENMP
+#pragma omp critical(nno_w960)
+#endif
+    {
+        if (!g_w960_ready) {
+            const double pi = 3.14159265358979323846264338327950288;
+            for (int k = 0; k < 960; k++) {
+                g_w960_re[k] = cos(-2.0 * pi * (double)k / 960.0);
+                g_w960_im[k] = sin(-2.0 * pi * (double)k / 960.0);
+            }
+            g_w960_ready = 1;
+        }
+    }
+}
+
 /* forward (e^{-i}) unnormalised 480-point complex FFT, result in buf a */
 static void cfft480(cpx *a, cpx *b) {
-    static const int radices[5] = {4, 4, 5, 3, 2};
+    static const int radices_a[5] = {4, 4, 5, 3, 2}, radices_b[5] = {2, 3, 5, 4, 4};
+    const int *radices = g_fft_mode == 2 ? radices_b : radices_a;
     int n = 480, s = 1;
     cpx *x = a, *y = b;
     for (int i = 0; i < 5; i++) {
@@ -157,6 +184,22 @@ static void cfft480(cpx *a, cpx *b) {
 
 void nno_rfft960(const float *in, float *ore, float *oim) {
     ensure_tables();
+    if (g_fft_mode == 1) {
+        ensure_w960();
+        for (int k = 0; k <= 480; k++) {
+            double sr = 0.0, si = 0.0;
+            for (int n = 0; n < 960; n++) {
+                const int idx = (k * n) % 960;
+                sr += (double)in[n] * g_w960_re[idx];
+                si += (double)in[n] * g_w960_im[idx];
+            }
+            ore[k] = (float)sr;
+            oim[k] = (float)si;
+        }
+        oim[0] = 0.0f;
+        oim[480] = 0.0f;
+        return;
+    }
     cpx z[480], w[480];
     for (int n = 0; n < 480; n++) {
         z[n].re = in[2 * n];
@@ -182,6 +225,19 @@ void nno_rfft960(const float *in, float *ore, float *oim) {
 
 void nno_irfft960(const float *re, const float *im, float *out) {
     ensure_tables();
+    if (g_fft_mode == 1) {
+        /* unnormalised inverse of a real signal's half spectrum; imaginary parts of DC / Nyquist ignored (realfft) */
+        ensure_w960();
+        for (int n = 0; n < 960; n++) {
+            double acc = (double)re[0] + ((n & 1) ? -(double)re[480] : (double)re[480]);
+            for (int k = 1; k < 480; k++) {
+                const int idx = (k * n) % 960; /* e^{+i} = conj of the table entry */
+                acc += 2.0 * ((double)re[k] * g_w960_re[idx] + (double)im[k] * g_w960_im[idx]);
+            }
+            out[n] = (float)acc;
+        }
+        return;
+    }
     cpx z[480], w[480];
     for (int k = 0; k < 480; k++) {
         /* imag parts of DC / Nyquist are ignored, as realfft does */

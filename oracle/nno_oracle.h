@@ -65,6 +65,9 @@ void nno_get_taps(const nno_state *s, nno_taps *taps);
 void nno_rfft960(const float *in960, float *out_re481, float *out_im481);
 void nno_irfft960(const float *re481, const float *im481, float *out960);
 int32_t nno_pitch_only(nno_state *s, const float *buf1728);
+/* FFT variant of every later transform (process-wide; test aid): 0 = f32 Stockham 4,4,5,3,2 (default, the pinned
+ * oracle), 1 = f64 DFT sums rounded once, 2 = f32 Stockham 2,3,5,4,4. */
+void nno_set_fft_mode(int mode);
 float nno_tansig(float x);
 float nno_sigmoid(float x);
 

@@ -90,3 +90,41 @@ def test_batch_driver_matches_single(builtin_bytes, testing_raw):
         for f in range(20):
             o, v = st.process_frame(x[s, f])
             assert np.array_equal(o, r["out"][s, f]) and v == r["vad"][s, f] and st.taps().pitch == r["pitch"][s, f]
+
+
+def test_post_silence_is_ill_conditioned_for_any_f32_fft(builtin_bytes):
+    """SURVEY H6, demonstrated instead of asserted: signal -> 45 frames of digital zeros -> signal.  Right after the cut
+    the analysis window holds only the smooth tail of the high-pass filter, the upper bands sit at the rounding floor
+    of the FFT and the pitch-correlation features divide that floor by itself (src/features.rs:136-137); the GRUs
+    remember it.  Three CORRECT FFTs -- the pinned f32 Stockham (mode 0), an f64 DFT rounded once (mode 1) and the same
+    f32 Stockham with another radix order (mode 2) -- agree to ~5e-7 before the cut and differ by 1e-4 (whole batch) to
+    ~1e-3 (single streams) afterwards, VAD by a few 1e-4; the pitch period stays identical.  This is the yardstick for the
+    tolerance of tests/test_gpu_parity.py::test_silence_path_and_recovery (a third f32 FFT, on the GPU)."""
+    from conftest import synth_streams
+    B = 64
+    sig = synth_streams(B, 8, seed=11).reshape(B, 8, 480)
+    x = np.concatenate([sig, np.zeros((B, 45, 480), np.float32), sig], axis=1)
+    m = oracle.Model(builtin_bytes)
+    res = {}
+    try:
+        for mode in (0, 1, 2):
+            oracle.set_fft_mode(mode)
+            res[mode] = oracle.run_batch(m, x, n_threads=0)
+    finally:
+        oracle.set_fft_mode(0)
+
+    def rr(a, b, ax=None):
+        a = a.astype(np.float64); b = b.astype(np.float64)
+        return np.sqrt(((a - b) ** 2).sum(axis=ax) / np.maximum((b ** 2).sum(axis=ax), 1e-30))
+
+    for a, b in ((0, 1), (2, 1), (0, 2)):
+        assert np.array_equal(res[a]["pitch"], res[b]["pitch"])
+        assert rr(res[a]["out"][:, :8], res[b]["out"][:, :8]) <= 2e-6                   # before the cut: tight
+        after = rr(res[a]["out"][:, 53:], res[b]["out"][:, 53:])
+        per = rr(res[a]["out"][:, 53:], res[b]["out"][:, 53:], ax=(1, 2))
+        dv = np.abs(res[a]["vad"] - res[b]["vad"]).max()
+        assert 3e-5 <= after <= 1e-3, (a, b, after)                                       # >= 50x amplification, bounded
+        assert 2e-4 <= per.max() <= 5e-3, (a, b, per.max())                              # single streams reach ~1e-3
+        assert 5e-5 <= dv <= 2e-3, (a, b, dv)
+    for mode in (0, 1, 2):
+        assert not res[mode]["vad"][:, 30:53].any()                                       # silent frames: vad exactly 0

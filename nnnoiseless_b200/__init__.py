@@ -20,7 +20,7 @@ NB_BANDS = 22
 NB_FEATURES = 42
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnnnoiseless_b200.so")
+LIB_PATH = os.environ.get("NNB_LIB") or os.path.join(_HERE, "lib", "libnnnoiseless_b200.so")  # NNB_LIB: a build variant
 BUILTIN_WEIGHTS_PATH = os.path.join(_HERE, "data", "weights.rnn")
 
 # every symbol include/rnnoise.h declares (checked by tests/test_capi_symbols.py)

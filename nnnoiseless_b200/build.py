@@ -10,9 +10,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_obj")
+# NNB_VARIANT=prof builds a second library with the pitch kernel's clock64 phase profile compiled in
+# (lib/libnnnoiseless_b200_prof.so, selected at run time with NNB_LIB=<path>); the default build is untouched.
+VARIANT = os.environ.get("NNB_VARIANT", "")
+OBJ = os.path.join(HERE, "_obj" + ("_" + VARIANT if VARIANT else ""))
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libnnnoiseless_b200.so")
+LIB = os.path.join(LIBDIR, "libnnnoiseless_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
+VARIANT_FLAGS = {"": [], "prof": ["-DPITCH_PROFILE"]}[VARIANT]
 WEIGHTS = os.path.join(HERE, "data", "weights.rnn")
 BINDIR = os.path.join(HERE, "bin")
 CLI = os.path.join(BINDIR, "nnnoiseless-b200")
@@ -54,7 +58,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src + ".o")
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            cmd = [NVCC] + ARCH + COMMON + extra + os.environ.get("NNB_EXTRA_NVCC", "").split() + ["-c", s, "-o", o]
+            cmd = [NVCC] + ARCH + COMMON + extra + VARIANT_FLAGS + os.environ.get("NNB_EXTRA_NVCC", "").split() + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             logs.append(r.stderr)
             if r.returncode != 0:
@@ -78,7 +82,7 @@ def build(force=False, verbose=False):
         subprocess.run(cmd, check=True)
     # the command-line front-end (src/nnnoiseless.rs): a thin main() over rnnoise_denoise_files
     os.makedirs(BINDIR, exist_ok=True)
-    if force or _newer(CLI, [CLI_SRC, LIB] + hdrs):
+    if not VARIANT and (force or _newer(CLI, [CLI_SRC, LIB] + hdrs)):
         cmd = ["g++", "-O2", "-std=c++17", "-Wall", CLI_SRC, "-o", CLI, "-L" + LIBDIR, "-lnnnoiseless_b200",
                "-Wl,-rpath,$ORIGIN/../lib"]
         subprocess.run(cmd, check=True)

@@ -165,8 +165,9 @@ struct DeviceGuard {
 // exact.cu (compiled with -fmad=false: bit-exact pitch path)
 cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, long stream_stride, long sample_stride, int slot,
                              cudaStream_t st);
-// force_exact: every stream takes the order-exact recomputation paths (NNB_PITCH_EXACT=1: the test reference)
-cudaError_t launch_pitch(const BatchBuffers& b, int slot, bool force_exact, cudaStream_t st);
+// force_exact bit 0: every stream recomputes its coarse search order-exact, bit 1: its sub-harmonic ladder
+// (NNB_PITCH_EXACT=1 sets both: the test reference; 2 / 3 select one of them)
+cudaError_t launch_pitch(const BatchBuffers& b, int slot, int force_exact, cudaStream_t st);
 // spectral.cu
 cudaError_t launch_analysis(const BatchBuffers& b, const DeviceTables* tab, int slot, cudaStream_t st);
 cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride, long sample_stride,

@@ -364,7 +364,7 @@ struct RNNoiseBatch {
     UploadedMma umm;
     bool rnn_fp32 = false;  // NNB_RNN_FP32=1: CUDA-core FP32 GRU kernel instead of the tensor-core one (debug / comparison)
     bool serial = false;    // NNB_SERIAL=1: all stages on one stream (debug / comparison)
-    bool pitch_exact = false;  // NNB_PITCH_EXACT=1: every stream takes the pitch kernel's order-exact recomputation paths
+    int pitch_exact = 0;  // NNB_PITCH_EXACT=1: every stream takes the pitch kernel's order-exact recomputation paths (2: coarse only, 3: ladder only)
     unsigned long long frame = 0;  // frames processed so far (ring slot = frame % HIST_SLOTS, set = frame % PIPE_DEPTH)
     // host-call staging: kStageSlots frames of device memory, recycled while a call of any length streams through
     // (sized for the sample type in use only: float or int16)
@@ -469,7 +469,7 @@ int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) 
         const char* e2 = getenv("NNB_SERIAL");
         b->serial = e2 && e2[0] == '1';
         const char* e3 = getenv("NNB_PITCH_EXACT");
-        b->pitch_exact = e3 && e3[0] == '1';
+        b->pitch_exact = !e3 ? 0 : (e3[0] == '1' ? 3 : (e3[0] == '2' ? 1 : (e3[0] == '3' ? 2 : 0)));
     }
     const int SS = b->um.dm.state_size;
     if (dalloc(b, &u.hist, B * HIST_CAP) || dalloc(b, &u.hp_mem, B * 2) || dalloc(b, &u.synth_mem, B * FRAME_SIZE) ||

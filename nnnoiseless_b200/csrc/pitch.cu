@@ -72,7 +72,7 @@ constexpr int Y4_LD = 436;
 constexpr int XC_LD = 149;
 constexpr int YY_LD = 387;
 constexpr int IPR_LD = 31;
-constexpr int FX_LD = 11;
+constexpr int FX_LD = 17;  // two aligned 8-lag fine windows per stream
 constexpr int NGRP = (NL4 + 3) / 4;  // 37 lag groups of 4
 constexpr int CMAX = 8;              // coarse candidates recomputed exactly per stream
 constexpr int LAG_LD = 24;           // remove_doubling lags per stream: 1 + 2 * 11 (k <= 12 because t1 >= 30, t0 <= 383)
@@ -91,8 +91,9 @@ constexpr int OFF_AC = OFF_YN4 + SB * XC_LD;     // [5][SB]
 constexpr int OFF_LPC = OFF_AC + 5 * SB;         // [5][SB]
 constexpr int OFF_XX = OFF_LPC + 5 * SB;         // [SB]
 constexpr int OFF_BND = OFF_XX + SB;             // [3][SB]: sum x_lp4^2 | sum P[0..384)^2 | sum Y4[0..192)^2
-constexpr int OFF_IPR = OFF_BND + 3 * SB;        // [SB][31]
-constexpr int OFF_FX = OFF_IPR + SB * IPR_LD;    // [SB][11]
+constexpr int OFF_NZ = OFF_BND + 3 * SB;         // int [2][SB]: OR of the magnitude bits of P[384..864) | P[0..384)
+constexpr int OFF_IPR = OFF_NZ + 2 * SB;         // [SB][31]
+constexpr int OFF_FX = OFF_IPR + SB * IPR_LD;    // [SB][17]
 constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [5][SB]: best4, second4, t0, t, t1b
 constexpr int OFF_CTR = OFF_SI + 5 * SB;         // int [8]
 constexpr int OFF_LAGS = OFF_CTR + 8;            // int [SB][24]
@@ -109,8 +110,8 @@ constexpr int SMEM_FLOATS = OFF_CK + SB * CK_LD;
 constexpr int OFF_CAND = OFF_IPR;                  // int [SB][CMAX]
 constexpr int OFF_CEX = OFF_CAND + SB * CMAX;      // [SB][CMAX]
 constexpr int OFF_XT = OFF_CEX + SB * CMAX;        // int [SB * CMAX]
-constexpr int OFF_MB = OFF_XT + SB * CMAX;         // [2][SB]
-constexpr int OFF_NEEDX = OFF_MB + 2 * SB;         // int [SB]
+constexpr int OFF_MB = OFF_XT + SB * CMAX;         // [SB]: upper bound of every non-candidate score
+constexpr int OFF_NEEDX = OFF_MB + SB;             // int [SB]
 static_assert(OFF_NEEDX + SB <= OFF_SI, "selection scratch must fit in the IPR + FX region");
 static_assert(CK_N <= CK_LD, "checkpoint row too short");
 static_assert(YY_LD <= Y4_LD, "yy must fit in the Y4 region");
@@ -162,6 +163,29 @@ __device__ __forceinline__ float autocorr_lag(const float4* __restrict__ row) {
     return fa(c, d);
 }
 
+// celt_autocorr lags 0 and 4 in ONE code path: half-warp h = 0 sums p[j] p[j] (+ the tail p[860..863]^2), half-warp
+// h = 1 sums p[j] p[j+4] -- the second operand is simply the row shifted by one float4 (no tail for lag 4).
+__device__ __forceinline__ float autocorr_lag04(const float4* __restrict__ row, int h) {
+    const float4* r2 = row + h;
+    float c = 0.0f;
+#pragma unroll 5
+    for (int m = 0; m < (PB - 4) / 4; m++) {
+        const float4 x = row[m], y = r2[m];
+        c = fa(c, fm(x.x, y.x));
+        c = fa(c, fm(x.y, y.y));
+        c = fa(c, fm(x.z, y.z));
+        c = fa(c, fm(x.w, y.w));
+    }
+    const float4 w = row[(PB - 4) / 4];  // p[860..863]
+    float d = 0.0f;
+    if (h == 0) d = fa(fa(fa(fa(d, fm(w.x, w.x)), fm(w.y, w.y)), fm(w.z, w.z)), fm(w.w, w.w));
+    return fa(c, d);
+}
+
+// Barrier among a SUBSET of the block's warps (id 1..15; __syncthreads is id 0): the long serial chains run on their own
+// warps past the barriers of phases that do not need their result.
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // inner_prod(x, y, 480) of src/pitch.rs:225-244 for one (stream, lag) lane-task:
 // xr = aligned float4 row of x (pbuf + 384), y = pbuf + 384 - lag (unaligned scalars).
 __device__ __forceinline__ float inner_prod_480(const float4* __restrict__ xr, const float* __restrict__ y) {
@@ -204,6 +228,63 @@ __device__ __forceinline__ void inner_prod_window(const float4* __restrict__ xr,
     }
 #pragma unroll
     for (int c = 0; c < NLAG; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
+}
+
+// Four consecutive lags of inner_prod(x, y + lag, 480) starting at a 16-byte aligned y (128-bit reads only: lanes of
+// different streams hit different rows, conflict-free): acc[c][u] is the reference's accumulator u of lag c.
+__device__ __forceinline__ void inner_prod_window4_aligned(const float4* __restrict__ xr, const float4* __restrict__ yr, float* out) {
+    float acc[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[c][u] = 0.0f;
+    float4 w = yr[0];
+#pragma unroll 2
+    for (int m = 0; m < HALF_N / 4; m++) {
+        const float4 x = xr[m];
+        const float4 wn = yr[m + 1];
+        const float e[8] = {w.x, w.y, w.z, w.w, wn.x, wn.y, wn.z, wn.w};
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[c][u] = fa(acc[c][u], fm(xv[u], e[u + c]));
+        w = wn;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
+}
+
+// Sixteen consecutive coarse lags 16g..16g+15 of one stream, FMA (certified afterwards): one x and one y LDS.128 per 64
+// multiply-adds -- shared memory bandwidth, not the FP pipe, was the limit of the 4-lag version.
+__device__ __forceinline__ void coarse_group16(const float* __restrict__ y4row, int g, float* __restrict__ xcrow) {
+    const float4* xr = reinterpret_cast<const float4*>(y4row + HALF_MAX / 2);
+    const float4* yr = reinterpret_cast<const float4*>(y4row + 16 * g);
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) acc[c] = 0.0f;
+    float e[20];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float4 v = yr[q];
+        e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w;
+    }
+#pragma unroll 5  // the 20-float window rotates with period 5: no register moves at the back-edge
+    for (int m = 0; m < N4 / 4; m++) {
+        const float4 x = xr[m];
+        const float4 v = yr[m + 4];
+        e[16] = v.x; e[17] = v.y; e[18] = v.z; e[19] = v.w;
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int c = 0; c < 16; c++) acc[c] = ffma(xv[u], e[u + c], acc[c]);
+#pragma unroll
+        for (int q = 0; q < 16; q++) e[q] = e[q + 4];
+    }
+#pragma unroll
+    for (int c = 0; c < 16; c++)
+        if (16 * g + c < NL4) xcrow[16 * g + c] = acc[c];
 }
 
 // Four consecutive coarse lags 4g..4g+3 of one stream (src/pitch.rs:82, 296-363): every accumulator sums
@@ -273,6 +354,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     float* LPC = sm + OFF_LPC;
     float* XX = sm + OFF_XX;
     float* BND = sm + OFF_BND;
+    int* NZ = reinterpret_cast<int*>(sm + OFF_NZ);
     float* IPR = sm + OFF_IPR;
     float* FX = sm + OFF_FX;
     int* SI = reinterpret_cast<int*>(sm + OFF_SI);
@@ -347,18 +429,21 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     __syncthreads();
     PPROF(0);
 
-    // ---- Ph2: celt_autocorr, warp k = lag k, lane = stream ----
-    for (int k = warp; k < 5; k += NW) {
+    // ---- Ph2: celt_autocorr, lane = stream: warp 0 = lags 0 (lanes 0-15) and 4 (lanes 16-31), warps 1-3 = lags 1-3 ----
+    if (warp < 4) {
         const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
-        float v;
-        switch (k) {
-            case 0: v = autocorr_lag<0>(row); break;
-            case 1: v = autocorr_lag<1>(row); break;
-            case 2: v = autocorr_lag<2>(row); break;
-            case 3: v = autocorr_lag<3>(row); break;
-            default: v = autocorr_lag<4>(row); break;
+        if (warp == 0) {
+            const int h = lane >> 4;
+            AC[(4 * h) * SB + ls] = autocorr_lag04(row, h);
+        } else if (lane < SB) {  // lanes 16-31 stay off: a mirrored lane would double the shared-memory wavefronts
+            float v;
+            switch (warp) {
+                case 1: v = autocorr_lag<1>(row); break;
+                case 2: v = autocorr_lag<2>(row); break;
+                default: v = autocorr_lag<3>(row); break;
+            }
+            AC[warp * SB + ls] = v;
         }
-        AC[k * SB + ls] = v;
     }
     __syncthreads();
     PPROF(1);
@@ -446,36 +531,24 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     __syncthreads();
     PPROF(3);
 
-    // ---- Ph5: serial chains on three warps, then the coarse cross-correlation (FMA) on all warps ----
-    if (warp == NW - 2) {
-        // y_sq_norm of find_best_pitch(xcorr, y_lp4, 240) (src/pitch.rs:379-382, 401-402); YN4[i] = value seen at lag i
-        const float4* row = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD);
-        float y = 1.0f;
-#pragma unroll 4
-        for (int m = 0; m < N4 / 4; m++) {
-            const float4 v = row[m];
-            y = fa(y, fm(v.x, v.x));
-            y = fa(y, fm(v.y, v.y));
-            y = fa(y, fm(v.z, v.z));
-            y = fa(y, fm(v.w, v.w));
-        }
-        float* out = YN4 + ls * XC_LD;
-        out[0] = y;
-#pragma unroll 2
-        for (int m = 0; m < NGRP; m++) {
-            const float4 va = row[N4 / 4 + m], vb = row[m];
-            const float a[4] = {va.x, va.y, va.z, va.w}, b[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                y = fmaxf(fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d]))), 1.0f);
-                if (4 * m + d + 1 < XC_LD) out[4 * m + d + 1] = y;
-            }
-        }
-    } else if (warp == NW - 3) {
+    // ---- Warp roles from here on (NW = 8).  The two longest serial chains are taken off the critical path: they run on
+    // their own warps PAST the barriers of the phases that do not need their result (named barriers over subsets):
+    //   CKW (warp 5): fine running energy (needed in Ph8)           -- skips Ph5 .. Ph6b, rejoins before Ph8
+    //   YYW (warp 7): yy_lookup (needed by the ladder, Ph10)        -- leaves after Ph6x, rejoins before Ph9
+    //   G1 = all but CKW (7 warps, barrier 1): Ph5, Ph6a, Ph6x;  G2 = G1 without YYW (6 warps): Ph6b;
+    //   barrier 2 = G2 + CKW before Ph8;  barrier 0 = everybody.
+    constexpr int CKW = NW - 3, YNW = NW - 2, YYW = NW - 1;
+    constexpr int G1N = (NW - 1) * 32;
+    static_assert(NW == 8, "warp roles assume 8 warps");
+    const int g1idx = warp < CKW ? warp : warp - 1;   // 0..6 over G1
+    const int g1tid = g1idx * 32 + lane;
+    float* YY = Y4;  // yy_lookup reuses the 4x-decimated copy once the coarse search is over
+
+    if (warp == CKW) {
+      if (lane < SB) {
         // y_sq_norm of find_best_pitch(xcorr, y, 480) (the FINE search, src/pitch.rs:97): a 774-step chain that needs
-        // nothing but the whitened buffer, so it runs here, under the coarse cross-correlation, instead of after it.
-        // Only every 8th value is kept (CK[m] = value seen at fine lag 8 m); Ph8 replays the few steps it needs from
-        // the nearest checkpoint -- same operations in the same order, hence the same values.
+        // nothing but the whitened buffer.  Only every 8th value is kept (CK[m] = value seen at fine lag 8 m); Ph8 replays
+        // the few steps it needs from the nearest checkpoint -- same operations in the same order, hence the same values.
         const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
         float y = 1.0f;
 #pragma unroll 4
@@ -496,289 +569,319 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             for (int d = 0; d < 4; d++) y = fmaxf(fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d]))), 1.0f);
             if ((m & 1) == 1) ck[(m + 1) >> 1] = y;  // after 4 (m + 1) steps
         }
-    } else if (warp == NW - 1) {
-        // Four energies, one code path for both half-warps (h = lane >> 4):
-        //   h = 0: xx = inner_prod(x, x, 480) with its four interleaved accumulators (src/pitch.rs:133, 225-244: EXACT,
-        //          it reaches last_gain), then sum x_lp4^2 = Y4[192..432)
-        //   h = 1: sum P[0..384)^2, then sum Y4[0..192)^2          (the last three only bound rounding errors)
-        const int h = lane >> 4;
-        const float4* pr = reinterpret_cast<const float4*>(P + ls * P_LD) + (h ? 0 : HALF_MAX / 4);
-        const int np = h ? HALF_MAX / 4 : HALF_N / 4;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll 4
-        for (int m = 0; m < HALF_N / 4; m++) {
-            if (m < np) {
-                const float4 x = pr[m];
-                a0 = fa(a0, fm(x.x, x.x));
-                a1 = fa(a1, fm(x.y, x.y));
-                a2 = fa(a2, fm(x.z, x.z));
-                a3 = fa(a3, fm(x.w, x.w));
-            }
-        }
-        const float sp = fa(fa(fa(a0, a1), a2), a3);
-        const float4* yr = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD) + (h ? 0 : HALF_MAX / 8);
-        const int ny = h ? HALF_MAX / 8 : N4 / 4;
-        a0 = a1 = a2 = a3 = 0.0f;
-#pragma unroll 4
-        for (int m = 0; m < N4 / 4; m++) {
-            if (m < ny) {
-                const float4 x = yr[m];
-                a0 = fa(a0, fm(x.x, x.x));
-                a1 = fa(a1, fm(x.y, x.y));
-                a2 = fa(a2, fm(x.z, x.z));
-                a3 = fa(a3, fm(x.w, x.w));
-            }
-        }
-        const float sy = fa(fa(fa(a0, a1), a2), a3);
-        if (h == 0) {
-            XX[ls] = sp;
-            BND[0 * SB + ls] = sy;
-        } else {
-            BND[1 * SB + ls] = sp;
-            BND[2 * SB + ls] = sy;
-        }
-    }
-    // coarse xcorr, FMA: lane-task = (stream, group of 4 consecutive lags)
-    for (;;) {
-        int T = 0;
-        if (lane == 0) T = atomicAdd(&CTR[0], 1);
-        T = __shfl_sync(0xffffffffu, T, 0);
-        if (T * 32 >= SB * NGRP) break;
-        const int L = T * 32 + lane;
-        if (L < SB * NGRP) {
-            const int s = L / NGRP, g = L - s * NGRP;
-            coarse_group<false>(Y4 + s * Y4_LD, g, XC + s * XC_LD);
-        }
-    }
-    __syncthreads();
-    PPROF(4);
-
-    // ---- Ph6a: certified coarse selection, one warp per stream, lane = lags lane, lane + 32, ... (src/pitch.rs:83-84) ----
-    for (int s = warp; s < SB; s += NW) {
-        const float* xc = XC + s * XC_LD;
-        const float* yn = YN4 + s * XC_LD;
-        float cv[NSLOT], yv[NSLOT];
-#pragma unroll
-        for (int k = 0; k < NSLOT; k++) {
-            const int lag = lane + 32 * k;
-            cv[k] = lag < NL4 ? xc[lag] : 0.0f;
-            yv[k] = lag < NL4 ? yn[lag] : 1.0f;
-        }
-        // approximate top two by score c^2 / y (c > 0); "none" = (0, 1, -1)
-        float n1 = 0.0f, d1 = 1.0f, n2 = 0.0f, d2 = 1.0f;
-        int i1 = -1, i2 = -1;
-#pragma unroll
-        for (int k = 0; k < NSLOT; k++) {
-            const float num = cv[k] > 0.0f ? cv[k] * cv[k] : 0.0f;
-            const bool b1 = num * d1 > n1 * yv[k];
-            const bool b2 = num * d2 > n2 * yv[k];
-            if (b1) {
-                n2 = n1; d2 = d1; i2 = i1;
-                n1 = num; d1 = yv[k]; i1 = lane + 32 * k;
-            } else if (b2) {
-                n2 = num; d2 = yv[k]; i2 = lane + 32 * k;
-            }
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const float on1 = __shfl_xor_sync(0xffffffffu, n1, off), od1 = __shfl_xor_sync(0xffffffffu, d1, off);
-            const float on2 = __shfl_xor_sync(0xffffffffu, n2, off), od2 = __shfl_xor_sync(0xffffffffu, d2, off);
-            const int oi1 = __shfl_xor_sync(0xffffffffu, i1, off), oi2 = __shfl_xor_sync(0xffffffffu, i2, off);
-            if (on1 * d1 > n1 * od1) {            // the other side's best wins: second = max(my best, its second)
-                const bool c = on2 * d1 > n1 * od2;
-                n2 = c ? on2 : n1; d2 = c ? od2 : d1; i2 = c ? oi2 : i1;
-                n1 = on1; d1 = od1; i1 = oi1;
-            } else {                               // my best stays: second = max(my second, its best)
-                const bool c = on1 * d2 > n2 * od1;
-                n2 = c ? on1 : n2; d2 = c ? od1 : d2; i2 = c ? oi1 : i2;
-            }
-        }
-        const int f1 = __shfl_sync(0xffffffffu, i1, 0), f2 = __shfl_sync(0xffffffffu, i2, 0);
-        const float ex4 = BND[0 * SB + s], y4tot = BND[2 * SB + s] + ex4;
-        const float delta = KAPPA4 * sqrtf(ex4 * y4tot) * 1.001f;
-        int best = 0, second = 1, nc = 0;
-        bool cx = force_exact != 0, need = false;
-        if (!(delta < 1e30f)) {
-            cx = true;  // inf / nan
-        } else if (f1 < 0) {
-            if (delta != 0.0f) cx = true;  // else every c_i is exactly 0: the reference keeps its initial (0, 1)
-        } else if (f2 < 0 || f2 == f1) {
-            cx = true;
-        } else {
-            const float c1 = xc[f1], c2 = xc[f2], y1 = yn[f1], y2 = yn[f2];
-            const float a1 = c1 - delta, a2 = c2 - delta;
-            if (!(a1 > 0.0f) || !(a2 > 0.0f) || !(a2 * a2 > 1e-20f) || !(c1 < 1e18f)) {
-                cx = true;
-            } else {
-                float tn = a1 * a1, td = y1;  // T0 = min(lo_F1, lo_F2) as a fraction
-                if (a2 * a2 * td < tn * y2) {
-                    tn = a2 * a2;
-                    td = y2;
-                }
-                unsigned inmask = 0, masks[NSLOT];
-                float mn = 0.0f, md = 1.0f;  // M = max upper bound over the non-candidates
-#pragma unroll
-                for (int k = 0; k < NSLOT; k++) {
-                    const int lag = lane + 32 * k;
-                    const float b = fmaxf(cv[k] + delta, 0.0f);
-                    const float hn = b * b;
-                    const bool in_c = lag < NL4 && ((lag == f1 || lag == f2) || (hn * td * ETA1 >= tn * yv[k]));
-                    masks[k] = __ballot_sync(0xffffffffu, in_c);
-                    if (in_c) inmask |= 1u << k;
-                    if (lag < NL4 && !in_c && hn * md > mn * yv[k]) {
-                        mn = hn;
-                        md = yv[k];
-                    }
-                }
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const float omn = __shfl_xor_sync(0xffffffffu, mn, off), omd = __shfl_xor_sync(0xffffffffu, md, off);
-                    if (omn * md > mn * omd) {
-                        mn = omn;
-                        md = omd;
-                    }
-                }
-                mn = __shfl_sync(0xffffffffu, mn, 0);
-                md = __shfl_sync(0xffffffffu, md, 0);
-#pragma unroll
-                for (int k = 0; k < NSLOT; k++) nc += __popc(masks[k]);
-                if (nc > CMAX) {
-                    cx = true;
-                } else {
-                    int basek = 0;  // candidates in ascending lag order: slot-major, lane-minor
-#pragma unroll
-                    for (int k = 0; k < NSLOT; k++) {
-                        if ((inmask >> k) & 1u) CAND[s * CMAX + basek + __popc(masks[k] & ((1u << lane) - 1u))] = lane + 32 * k;
-                        basek += __popc(masks[k]);
-                    }
-                    const float b2 = c2 + delta;
-                    if (nc == 2 && a1 * a1 * y2 > b2 * b2 * y1 * ETA1) {
-                        best = f1;
-                        second = f2;
-                    } else {
-                        need = true;
-                    }
-                    if (lane == 0) {
-                        MB[s] = mn;
-                        MB[SB + s] = md;
-                    }
-                }
-            }
-        }
-        if (cx) need = false;
-        if (lane == 0) {
-            SI[0 * SB + s] = best;
-            SI[1 * SB + s] = second;
-            NEEDX[s] = need ? nc : 0;
-            if (cx) {
-                FLAG[s] = 1;
-                CXL[atomicAdd(&CTR[2], 1)] = s;
-            } else if (need) {
-                const int base = atomicAdd(&CTR[3], nc);
-                for (int i = 0; i < nc; i++) XT[base + i] = (s << 8) | i;
-            }
-        }
-    }
-    __syncthreads();
-    PPROF(5);
-
-    // ---- Ph6x: exact recomputation where the certificate failed.  Round 0: the candidates of the "need" streams and all
-    // 147 lags of the CXL streams; round 1: all lags of streams whose candidates turned out not to dominate. ----
-    for (int round = 0; round < 2; round++) {
-        const int ncx_lo = CTR[7], ncx = CTR[2], nx = round == 0 ? CTR[3] : 0;
-        if (ncx == ncx_lo && nx == 0) break;  // block-uniform
-        for (int L = tid; L < nx; L += NT) {
-            const int e = XT[L], s = e >> 8, pos = e & 255;
-            const int lag = CAND[s * CMAX + pos];
-            const float4* xr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + HALF_MAX / 2);
-            const float* yr = Y4 + s * Y4_LD + lag;
-            float c = 0.0f;  // src/pitch.rs:296-363: one accumulator per lag, j ascending
+      }
+    } else {
+        // ---- Ph5 (G1): two short serial jobs, then the coarse cross-correlation (FMA) ----
+        if (warp == YNW && lane < SB) {
+            // y_sq_norm of find_best_pitch(xcorr, y_lp4, 240) (src/pitch.rs:379-382, 401-402); YN4[i] = value seen at lag i
+            const float4* row = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD);
+            float y = 1.0f;
 #pragma unroll 4
             for (int m = 0; m < N4 / 4; m++) {
-                const float4 x = xr[m];
-                c = fa(c, fm(x.x, yr[4 * m]));
-                c = fa(c, fm(x.y, yr[4 * m + 1]));
-                c = fa(c, fm(x.z, yr[4 * m + 2]));
-                c = fa(c, fm(x.w, yr[4 * m + 3]));
+                const float4 v = row[m];
+                y = fa(y, fm(v.x, v.x));
+                y = fa(y, fm(v.y, v.y));
+                y = fa(y, fm(v.z, v.z));
+                y = fa(y, fm(v.w, v.w));
             }
-            CEX[s * CMAX + pos] = c;
-        }
-        for (int L = tid; L < (ncx - ncx_lo) * 40; L += NT) {
-            const int i = L / 40, g = L - i * 40;
-            if (g < NGRP) {
-                const int s = CXL[ncx_lo + i];
-                coarse_group<true>(Y4 + s * Y4_LD, g, XC + s * XC_LD);
+            float* out = YN4 + ls * XC_LD;
+            out[0] = y;
+#pragma unroll 2
+            for (int m = 0; m < NGRP; m++) {
+                const float4 va = row[N4 / 4 + m], vb = row[m];
+                const float a[4] = {va.x, va.y, va.z, va.w}, b[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+                for (int d = 0; d < 4; d++) {
+                    y = fmaxf(fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d]))), 1.0f);
+                    if (4 * m + d + 1 < XC_LD) out[4 * m + d + 1] = y;
+                }
+            }
+        } else if (warp == YYW) {
+            // Four energies, one code path for both half-warps (h = lane >> 4):
+            //   h = 0: xx = inner_prod(x, x, 480) with its four interleaved accumulators (src/pitch.rs:133, 225-244: EXACT,
+            //          it reaches last_gain), then sum x_lp4^2 = Y4[192..432)
+            //   h = 1: sum P[0..384)^2, then sum Y4[0..192)^2          (the last three only bound rounding errors)
+            const int h = lane >> 4;
+            const float4* pr = reinterpret_cast<const float4*>(P + ls * P_LD) + (h ? 0 : HALF_MAX / 4);
+            const int np = h ? HALF_MAX / 4 : HALF_N / 4;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            unsigned nz = 0;  // does the row hold anything but (signed) zeros?  (a sum of squares may underflow to 0)
+#pragma unroll 4
+            for (int m = 0; m < HALF_N / 4; m++) {
+                if (m < np) {
+                    const float4 x = pr[m];
+                    a0 = fa(a0, fm(x.x, x.x));
+                    a1 = fa(a1, fm(x.y, x.y));
+                    a2 = fa(a2, fm(x.z, x.z));
+                    a3 = fa(a3, fm(x.w, x.w));
+                    nz |= __float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) | __float_as_uint(x.w);
+                }
+            }
+            NZ[h * SB + ls] = (int)(nz & 0x7fffffffu);
+            const float sp = fa(fa(fa(a0, a1), a2), a3);
+            const float4* yr = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD) + (h ? 0 : HALF_MAX / 8);
+            const int ny = h ? HALF_MAX / 8 : N4 / 4;
+            a0 = a1 = a2 = a3 = 0.0f;
+#pragma unroll 4
+            for (int m = 0; m < N4 / 4; m++) {
+                if (m < ny) {
+                    const float4 x = yr[m];
+                    a0 = fa(a0, fm(x.x, x.x));
+                    a1 = fa(a1, fm(x.y, x.y));
+                    a2 = fa(a2, fm(x.z, x.z));
+                    a3 = fa(a3, fm(x.w, x.w));
+                }
+            }
+            const float sy = fa(fa(fa(a0, a1), a2), a3);
+            if (h == 0) {
+                XX[ls] = sp;
+                BND[0 * SB + ls] = sy;
+            } else {
+                BND[1 * SB + ls] = sp;
+                BND[2 * SB + ls] = sy;
             }
         }
-        __syncthreads();
-        if (warp == 0 && lane < SB) {
-            const int s = lane;
+        // coarse xcorr, FMA: lane-task = (stream, group of 16 consecutive lags): 160 tasks = warps 0-4 exactly
+        if (warp < CKW) {
+            const int L = warp * 32 + lane;
+            const int s = L / 10, g = L - s * 10;
+            coarse_group16(Y4 + s * Y4_LD, g, XC + s * XC_LD);
+        }
+        bar_sync(1, G1N);
+        PPROF(4);
+
+        // ---- Ph6a (G1): certified coarse selection, one warp per stream, lane = lags lane, lane + 32, ... (src/pitch.rs:83-84) ----
+        for (int s = g1idx; s < SB; s += NW - 1) {
             const float* xc = XC + s * XC_LD;
             const float* yn = YN4 + s * XC_LD;
-            const int fl = FLAG[s];
-            if ((fl & 1) && !(fl & 4)) {
-                // the reference's scan over all lags on exact values
-                BestTwo b2;
-#pragma unroll 7
-                for (int i = 0; i < NL4; i++) b2.consider(i, xc[i], yn[i]);
-                SI[0 * SB + s] = b2.best;
-                SI[1 * SB + s] = b2.second;
-                FLAG[s] = fl | 4;
-            } else if (round == 0 && NEEDX[s] > 0) {
-                const int nc = NEEDX[s];
-                const float mn = MB[s], md = MB[SB + s];
-                BestTwo b2;
-                bool ok = true;
-                for (int k = 0; k < nc; k++) {
-                    const int lag = CAND[s * CMAX + k];
-                    const float c = CEX[s * CMAX + k], ysq = yn[lag];
-                    // every candidate must beat the upper bound of every non-candidate robustly
-                    if (!(c > 0.0f) || !(c * c * md > mn * ysq * ETA1)) ok = false;
-                    b2.consider(lag, c, ysq);
+            float cv[NSLOT], yv[NSLOT];
+#pragma unroll
+            for (int k = 0; k < NSLOT; k++) {
+                const int lag = lane + 32 * k;
+                cv[k] = lag < NL4 ? xc[lag] : 0.0f;
+                yv[k] = lag < NL4 ? yn[lag] : 1.0f;
+            }
+            // approximate top two by score c^2 / y (c > 0): ANY two distinct lags keep the certificate sound, so the scores
+            // may be rounded freely (fast division) and the warp maxima taken on their bit patterns (scores >= 0)
+            float m1 = 0.0f, m2 = 0.0f;
+            int k1 = 0, k2 = 0;
+#pragma unroll
+            for (int k = 0; k < NSLOT; k++) {
+                const float r = cv[k] > 0.0f ? __fdividef(cv[k] * cv[k], yv[k]) : 0.0f;
+                if (r > m1) {
+                    m2 = m1; k2 = k1;
+                    m1 = r; k1 = k;
+                } else if (r > m2) {
+                    m2 = r; k2 = k;
                 }
-                if (ok) {
+            }
+            const unsigned M1 = __reduce_max_sync(0xffffffffu, __float_as_uint(m1));
+            const unsigned w1 = __ballot_sync(0xffffffffu, __float_as_uint(m1) == M1);
+            const int L1 = __ffs(w1) - 1;
+            int f1 = __shfl_sync(0xffffffffu, lane + 32 * k1, L1);
+            if (M1 == 0u) f1 = -1;
+            const float c2m = lane == L1 ? m2 : m1;
+            const int c2k = lane == L1 ? k2 : k1;
+            const unsigned M2 = __reduce_max_sync(0xffffffffu, __float_as_uint(c2m));
+            const unsigned w2 = __ballot_sync(0xffffffffu, __float_as_uint(c2m) == M2);
+            const int L2 = __ffs(w2) - 1;
+            int f2 = __shfl_sync(0xffffffffu, lane + 32 * c2k, L2);
+            if (M2 == 0u) f2 = -1;
+            const float ex4 = BND[0 * SB + s], y4tot = BND[2 * SB + s] + ex4;
+            const float delta = KAPPA4 * sqrtf(ex4 * y4tot) * 1.001f;
+            int best = 0, second = 1, nc = 0;
+            bool cx = (force_exact & 1) != 0, need = false;
+            if (!(delta < 1e30f)) {
+                cx = true;  // inf / nan
+            } else if ((NZ[s] | NZ[SB + s]) == 0) {
+                // the whitened history is exactly zero: every c_i is exactly 0 and the reference keeps its initial (0, 1)
+            } else if (!(ex4 > 1e-18f) || !(y4tot > 1e-18f) || !(ex4 * y4tot * (y4tot + 1.0f) < 1e37f)) {
+                // Outside the range where find_best_pitch's own products c^2 y (src/pitch.rs:386-388) stay finite and normal
+                // (c^2 <= ex4 y4tot by Cauchy-Schwarz, 1 <= y <= y4tot + 1): there the reference selects on signs alone
+                // (underflow) or gets stuck on inf > inf (overflow, amplitudes beyond ~2.5x the int16 range it documents).
+                // Parity means reproducing that, so those streams take the order-exact path.  Inside the range every
+                // score below is a finite, normal quotient.
+                cx = true;
+            } else if (f1 < 0 || f2 < 0 || f2 == f1) {
+                cx = true;
+            } else {
+                const float c1 = xc[f1], c2 = xc[f2], y1 = yn[f1], y2 = yn[f2];
+                const float a1 = c1 - delta, a2 = c2 - delta;
+                if (!(a1 > 0.0f) || !(a2 > 0.0f) || !(a1 * a1 > 1e-20f) || !(a2 * a2 > 1e-20f)) {
+                    cx = true;
+                } else {
+                    // scores as quotients (fast division: its 2 ulp are far inside the slack ETA1 of every comparison)
+                    const float lo1 = __fdividef(a1 * a1, y1), lo2 = __fdividef(a2 * a2, y2);
+                    const float b1 = c1 + delta, b2 = c2 + delta;
+                    const float hi1 = __fdividef(b1 * b1, y1), hi2 = __fdividef(b2 * b2, y2);
+                    const float t0s = fminf(lo1, lo2);  // T0 = min(lo_F1, lo_F2)
+                    unsigned inmask = 0, masks[NSLOT];
+                    float hmax = 0.0f;  // M = max upper bound over the non-candidates
+#pragma unroll
+                    for (int k = 0; k < NSLOT; k++) {
+                        const int lag = lane + 32 * k;
+                        const float b = fmaxf(cv[k] + delta, 0.0f);
+                        const float hs = __fdividef(b * b, yv[k]);
+                        const bool in_c = lag < NL4 && ((lag == f1 || lag == f2) || (hs * ETA1 >= t0s));
+                        masks[k] = __ballot_sync(0xffffffffu, in_c);
+                        if (in_c) inmask |= 1u << k;
+                        if (lag < NL4 && !in_c) hmax = fmaxf(hmax, hs);
+                    }
+                    const float mbound = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hmax))) * ETA1;
+#pragma unroll
+                    for (int k = 0; k < NSLOT; k++) nc += __popc(masks[k]);
+                    if (nc > CMAX) {
+                        cx = true;
+                    } else {
+                        int basek = 0;  // candidates in ascending lag order: slot-major, lane-minor
+#pragma unroll
+                        for (int k = 0; k < NSLOT; k++) {
+                            if ((inmask >> k) & 1u) CAND[s * CMAX + basek + __popc(masks[k] & ((1u << lane) - 1u))] = lane + 32 * k;
+                            basek += __popc(masks[k]);
+                        }
+                        if (nc == 2 && lo1 > hi2 * ETA1) {         // lo_F1 > hi_F2 (1 + eta)
+                            best = f1;
+                            second = f2;
+                        } else if (nc == 2 && lo2 > hi1 * ETA1) {  // the rounded scores had them the other way round
+                            best = f2;
+                            second = f1;
+                        } else {
+                            need = true;
+                        }
+                        if (lane == 0) MB[s] = mbound;
+                    }
+                }
+            }
+            if (cx) need = false;
+            if (lane == 0) {
+                SI[0 * SB + s] = best;
+                SI[1 * SB + s] = second;
+                NEEDX[s] = need ? nc : 0;
+                if (cx) {
+                    FLAG[s] = 1;
+                    CXL[atomicAdd(&CTR[2], 1)] = s;
+                } else if (need) {
+                    const int base = atomicAdd(&CTR[3], nc);
+                    for (int i = 0; i < nc; i++) XT[base + i] = (s << 8) | i;
+                }
+            }
+        }
+        bar_sync(1, G1N);
+        PPROF(5);
+
+        // ---- Ph6x (G1): exact recomputation where the certificate failed.  Round 0: the candidates of the "need" streams and
+        // all 147 lags of the CXL streams; round 1: all lags of streams whose candidates turned out not to dominate. ----
+        for (int round = 0; round < 2; round++) {
+            const int ncx_lo = CTR[7], ncx = CTR[2], nx = round == 0 ? CTR[3] : 0;
+            if (ncx == ncx_lo && nx == 0) break;  // uniform over G1
+            for (int L = g1tid; L < nx; L += G1N) {
+                const int e = XT[L], s = e >> 8, pos = e & 255;
+                const int lag = CAND[s * CMAX + pos];
+                const float4* xr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + HALF_MAX / 2);
+                const float* yr = Y4 + s * Y4_LD + lag;
+                float c = 0.0f;  // src/pitch.rs:296-363: one accumulator per lag, j ascending
+#pragma unroll 4
+                for (int m = 0; m < N4 / 4; m++) {
+                    const float4 x = xr[m];
+                    c = fa(c, fm(x.x, yr[4 * m]));
+                    c = fa(c, fm(x.y, yr[4 * m + 1]));
+                    c = fa(c, fm(x.z, yr[4 * m + 2]));
+                    c = fa(c, fm(x.w, yr[4 * m + 3]));
+                }
+                CEX[s * CMAX + pos] = c;
+            }
+            for (int L = g1tid; L < (ncx - ncx_lo) * 40; L += G1N) {
+                const int i = L / 40, g = L - i * 40;
+                if (g < NGRP) {
+                    const int s = CXL[ncx_lo + i];
+                    coarse_group<true>(Y4 + s * Y4_LD, g, XC + s * XC_LD);
+                }
+            }
+            bar_sync(1, G1N);
+            if (warp == 0 && lane < SB) {
+                const int s = lane;
+                const float* xc = XC + s * XC_LD;
+                const float* yn = YN4 + s * XC_LD;
+                const int fl = FLAG[s];
+                if ((fl & 1) && !(fl & 4)) {
+                    // the reference's scan over all lags on exact values
+                    BestTwo b2;
+#pragma unroll 7
+                    for (int i = 0; i < NL4; i++) b2.consider(i, xc[i], yn[i]);
                     SI[0 * SB + s] = b2.best;
                     SI[1 * SB + s] = b2.second;
-                } else {
-                    FLAG[s] = fl | 1;
-                    CXL[atomicAdd(&CTR[2], 1)] = s;
+                    FLAG[s] = fl | 4;
+                } else if (round == 0 && NEEDX[s] > 0) {
+                    const int nc = NEEDX[s];
+                    const float mbound = MB[s];
+                    BestTwo b2;
+                    bool ok = true;
+                    for (int k = 0; k < nc; k++) {
+                        const int lag = CAND[s * CMAX + k];
+                        const float c = CEX[s * CMAX + k], ysq = yn[lag];
+                        // every candidate must beat the upper bound of every non-candidate robustly
+                        if (!(c > 0.0f) || !(__fdividef(c * c, ysq) > mbound * ETA1)) ok = false;
+                        b2.consider(lag, c, ysq);
+                    }
+                    if (ok) {
+                        SI[0 * SB + s] = b2.best;
+                        SI[1 * SB + s] = b2.second;
+                    } else {
+                        FLAG[s] = fl | 1;
+                        CXL[atomicAdd(&CTR[2], 1)] = s;
+                    }
                 }
             }
+            bar_sync(1, G1N);
+            if (g1tid == 0) CTR[7] = ncx;
+            bar_sync(1, G1N);
         }
-        __syncthreads();
-        if (tid == 0) CTR[7] = ncx;
-        __syncthreads();
-    }
-    PPROF(6);
+        PPROF(6);
 
-    // ---- Ph6b: the two 5-lag fine windows of every stream (src/pitch.rs:88-96), each split into a 3-lag and a
-    // 2-lag sliding window so that two warps share the work.  lane-task = (stream, window): lags i0c .. i0c+4, i0c =
-    // window start clamped into the valid range; which of them count as candidates is decided in Ph8. ----
-    if (warp == 2 || warp == 3) {
-        for (int L = lane; L < 2 * SB; L += 32) {
-            const int s = L >> 1, wdw = L & 1;
-            const int ctr = 2 * SI[wdw * SB + s];
-            const int i0c = min(max(ctr - 2, 0), NL2 - 5);
-            const float* prow = P + s * P_LD;
-            const float4* xr = reinterpret_cast<const float4*>(prow + HALF_MAX);
-            if (warp == 2) {
-                float out[3];
-                inner_prod_window<3>(xr, prow + i0c, out);
+        if (warp == YYW) {
+          if (lane < SB) {
+            // yy_lookup (src/pitch.rs:135-142): stored clamped at 0, carried unclamped; i = 1..384 walks the rows downwards.
+            // Runs beside the fine search (the 4x-decimated copy it overwrites is dead after Ph6x).
+            const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
+            float* out = YY + ls * YY_LD;
+            float y = XX[ls];
+            out[0] = y;
+#pragma unroll 2
+            for (int m = 0; m < HALF_MAX / 4; m++) {
+                const float4 va = row[HALF_MAX / 4 - 1 - m];              // p[380-4m .. 383-4m]
+                const float4 vb = row[(HALF_MAX + HALF_N) / 4 - 1 - m];   // p[860-4m .. 863-4m]
+                const float a[4] = {va.w, va.z, va.y, va.x}, b[4] = {vb.w, vb.z, vb.y, vb.x};
 #pragma unroll
-                for (int c = 0; c < 3; c++) FX[s * FX_LD + wdw * 5 + c] = fmaxf(out[c], -1.0f);
-            } else {
-                float out[2];
-                inner_prod_window<2>(xr, prow + i0c + 3, out);
+                for (int d = 0; d < 4; d++) {
+                    y = fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d])));
+                    out[4 * m + d + 1] = fmaxf(y, 0.0f);
+                }
+            }
+          }
+        } else {
+            // ---- Ph6b (G2): the two 5-lag fine windows of every stream (src/pitch.rs:88-96).  Each window i0c .. i0c+4 (i0c =
+            // start clamped into the valid range) lies inside the ALIGNED 8 lags a .. a+7, a = i0c & ~3, computed as two 4-lag
+            // sliding windows on 128-bit reads: 64 lane-tasks (stream, window, half) = warps 0 and 1.  Which lags count as
+            // candidates is decided in Ph8. ----
+            if (warp < 2) {
+                const int L = warp * 32 + lane;
+                const int s = L >> 2, wdw = (L >> 1) & 1, half = L & 1;
+                const int ctr = 2 * SI[wdw * SB + s];
+                const int a = min(max(ctr - 2, 0), NL2 - 5) & ~3;
+                const float* prow = P + s * P_LD;
+                float out[4];
+                inner_prod_window4_aligned(reinterpret_cast<const float4*>(prow + HALF_MAX),
+                                           reinterpret_cast<const float4*>(prow + a + 4 * half), out);
 #pragma unroll
-                for (int c = 0; c < 2; c++) FX[s * FX_LD + wdw * 5 + 3 + c] = fmaxf(out[c], -1.0f);
+                for (int c = 0; c < 4; c++) FX[s * FX_LD + wdw * 8 + half * 4 + c] = fmaxf(out[c], -1.0f);
             }
         }
     }
-    __syncthreads();
+    if (warp != YYW) bar_sync(2, G1N);  // G2 + CKW: FX and CK complete
     PPROF(7);
 
     // ---- Ph8: fine best + pseudo-interpolation (src/pitch.rs:97-114), lane = stream ----
-    if (warp == 0) {
+    if (warp == 0 && lane < SB) {
         const int best4 = SI[0 * SB + ls], second4 = SI[1 * SB + ls];
         const float* fx = FX + ls * FX_LD;
         // fine running energy at lag i, replayed from the nearest checkpoint at or below it (lags are asked in
@@ -805,8 +908,8 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         // xcorr at fine lag i: computed iff |i - 2 best| <= 2 or |i - 2 second| <= 2 (src/pitch.rs:90-95), else 0
         auto xcf = [&](int i) -> float {
             if (i < 0 || i >= NL2) return 0.0f;
-            if (abs(i - cA) <= 2) return fx[i - baseA];
-            if (abs(i - cB) <= 2) return fx[5 + i - baseB];
+            if (abs(i - cA) <= 2) return fx[i - (baseA & ~3)];
+            if (abs(i - cB) <= 2) return fx[8 + i - (baseB & ~3)];
             return 0.0f;
         };
         BestTwo b2;
@@ -828,7 +931,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         // The lags remove_doubling needs (src/pitch.rs:134,152-168): t0, then for k = 2.. while t1 >= min_period the
         // pair (t1, t1b); IPR[stream][1 + position] = inner_prod(x, x - lag, 480).
         // (k is a compile-time constant in the unrolled loops below: the divisions by 2k become multiply-shifts)
-        if (lane < SB) {
+        {
             SI[2 * SB + ls] = t0;
             int* lg = LAGS + ls * LAG_LD;
             lg[0] = t0;
@@ -847,31 +950,12 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             NLAG[ls] = 1 + 2 * nk;
         }
     }
-    __syncthreads();
+    __syncthreads();  // everybody: LAGS written, yy_lookup complete
     PPROF(8);
 
-    // ---- Ph9: yy_lookup chain (warp NW-1 first) + remove_doubling inner products, FMA, one WARP per stream:
-    // lane l owns samples 15 l .. 15 l + 14 of x (registers) and of every lagged window (scalar reads at stride 15:
-    // conflict-free for any lag); eight lags share one transposed shuffle reduction. ----
-    float* YY = Y4;  // the 4x-decimated copy is dead from here on
-    if (warp == NW - 1) {
-        // yy_lookup (src/pitch.rs:135-142): stored clamped at 0, carried unclamped; i = 1..384 walks the rows downwards
-        const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
-        float* out = YY + ls * YY_LD;
-        float y = XX[ls];
-        out[0] = y;
-#pragma unroll 2
-        for (int m = 0; m < HALF_MAX / 4; m++) {
-            const float4 va = row[HALF_MAX / 4 - 1 - m];              // p[380-4m .. 383-4m]
-            const float4 vb = row[(HALF_MAX + HALF_N) / 4 - 1 - m];   // p[860-4m .. 863-4m]
-            const float a[4] = {va.w, va.z, va.y, va.x}, b[4] = {vb.w, vb.z, vb.y, vb.x};
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                y = fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d])));
-                out[4 * m + d + 1] = fmaxf(y, 0.0f);
-            }
-        }
-    }
+    // ---- Ph9: remove_doubling inner products, FMA, one WARP per stream: lane l owns samples 15 l .. 15 l + 14 of x
+    // (registers) and of every lagged window (scalar reads at stride 15: conflict-free for any lag); eight lags share
+    // one transposed shuffle reduction. ----
     for (;;) {
         int s = 0;
         if (lane == 0) s = atomicAdd(&CTR[1], 1);
@@ -921,7 +1005,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     PPROF(9);
 
     // ---- Ph10a: the sub-harmonic ladder (src/pitch.rs:144-203) on the fast inner products, every decision certified ----
-    // pass == 0: fast values with margins; pass == 1 (only for streams in RXL): the same code on exact values.
+    // exact == false: fast values with margins; exact == true (only for streams in RXL): the same code on exact values.
     auto ladder = [&](bool exact, int& t_out, int& t1b_out, bool& uncertain) {
         const float* ipr = IPR + ls * IPR_LD;
         const float* yy = YY + ls * YY_LD;
@@ -972,12 +1056,12 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         t_out = t;
         t1b_out = t1bs;
     };
-    if (warp == 0) {
+    if (warp == 0 && lane < SB) {
         int t, t1b;
         bool unc;
         ladder(false, t, t1b, unc);
-        if (force_exact) unc = true;
-        if (lane < SB) {
+        if (force_exact & 2) unc = true;
+        {
             SI[3 * SB + ls] = t;
             SI[4 * SB + ls] = t1b;
             if (unc) {
@@ -989,7 +1073,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     __syncthreads();
     PPROF(10);
 
-    // ---- Ph10x: exact inner products (src/pitch.rs:225-244) of the streams whose ladder could not be certified ----
+    // ---- Ph10x: streams whose ladder could not be certified: exact inner products (src/pitch.rs:225-244), exact replay ----
     {
         const int nrx = CTR[4];
         if (nrx > 0) {  // block-uniform
@@ -1003,27 +1087,35 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
                 }
             }
             __syncthreads();
+            if (warp == 0 && lane < SB && (FLAG[ls] & 2)) {
+                int t, t1b;
+                bool dummy;
+                ladder(true, t, t1b, dummy);
+                {
+                    SI[3 * SB + ls] = t;
+                    SI[4 * SB + ls] = t1b;
+                }
+            }
+            __syncthreads();
         }
     }
 
-    // ---- Ph10b-12: exact replay where needed, then what reaches the state and the output, always order-exact: the +-1
-    // refinement (src/pitch.rs:205-218) and last_gain (:199-203).  Lanes 0-15 slide a 3-lag window over lags t+1, t, t-1
-    // of their stream; lanes 16-31 run the SAME code at lag t1b (the second inner product behind best_xy). ----
-    if (warp == 0) {
-        int t = SI[3 * SB + ls], t1b = SI[4 * SB + ls];
-        if (FLAG[ls] & 2) {
-            bool dummy;
-            ladder(true, t, t1b, dummy);
-        }
-        const int t0 = SI[2 * SB + ls];
+    // ---- Ph11: what reaches the state and the output is always order-exact: the +-1 refinement (src/pitch.rs:205-218)
+    // and last_gain (:199-203).  Four single-lag lane-tasks per stream -- lags t+1, t, t-1 and t1b (the second inner
+    // product behind best_xy) -- on two warps, then one lane per stream finishes. ----
+    float* XF = FX;  // [SB][4] in the (dead) fine-window buffer
+    if (warp < 2) {
+        const int s = 8 * warp + (lane >> 2), j = lane & 3;
+        const int t = SI[3 * SB + s], t1b = SI[4 * SB + s];
+        const float* prow = P + s * P_LD;
+        XF[s * FX_LD + j] = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (j < 3 ? t + 1 - j : t1b));
+    }
+    __syncthreads();
+    if (warp == 0 && lane < SB) {
+        const int t = SI[3 * SB + ls], t1b = SI[4 * SB + ls], t0 = SI[2 * SB + ls];
         const float* yy = YY + ls * YY_LD;
         const float xx = XX[ls];
-        const bool hi = lane >= SB;
-        float xc3[3];
-        const float* prow = P + ls * P_LD;
-        inner_prod_window<3>(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (hi ? t1b : t + 1), xc3);
-        const float x_0 = xc3[2], x_1 = xc3[1], x_2 = xc3[0];  // lanes 0-15: window slot c <-> lag t + 1 - c
-        const float ipb = __shfl_down_sync(0xffffffffu, xc3[0], SB);  // lanes 16-31: slot 0 <-> lag t1b
+        const float x_2 = XF[ls * FX_LD + 0], x_1 = XF[ls * FX_LD + 1], x_0 = XF[ls * FX_LD + 2], ipb = XF[ls * FX_LD + 3];  // x_k: lag t - 1 + k
         float best_xy, best_yy;
         if (t == t0) {  // no sub-harmonic accepted (an accepted t1 is always < t0)
             best_xy = x_1;
@@ -1072,7 +1164,7 @@ extern "C" void nnb_pitch_prof_read(unsigned long long* out16, int reset) {
 }
 #endif
 
-cudaError_t launch_pitch(const BatchBuffers& b, int slot, bool force_exact, cudaStream_t st) {
+cudaError_t launch_pitch(const BatchBuffers& b, int slot, int force_exact, cudaStream_t st) {
     static std::atomic<unsigned long long> attr_devs{0};  // bit d: attribute set on device d
     const size_t smem = sizeof(float) * SMEM_FLOATS;
     int dev = 0;
@@ -1084,7 +1176,7 @@ cudaError_t launch_pitch(const BatchBuffers& b, int slot, bool force_exact, cuda
         if (dev < 64) attr_devs.fetch_or(1ull << dev, std::memory_order_release);
     }
     const int grid = (b.n_streams + SB - 1) / SB;
-    pitch_kernel<<<grid, NT, smem, st>>>(b.hist, b.last_period, b.last_gain, b.pitch, b.n_streams, hist_base(slot), force_exact ? 1 : 0,
+    pitch_kernel<<<grid, NT, smem, st>>>(b.hist, b.last_period, b.last_gain, b.pitch, b.n_streams, hist_base(slot), force_exact,
                                          b.pitch_stats);
     return cudaGetLastError();
 }

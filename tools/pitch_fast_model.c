@@ -74,44 +74,49 @@ static int coarse_fast(const float *x4, const float *y4, int *best, int *second,
     for (int i = 0; i < NL4; i++) ch[i] = fma_dot(x4, y4 + i, N4);
     const float delta = KAPPA4 * sqrtf(ex * ytot) * 1.001f;
     if (!(delta < 1e30f)) { st->flag_nonfinite++; return 1; }   /* inf / nan */
-    /* approximate top two by score ch^2 / yn (ch > 0) */
+    int anynz = 0;
+    for (int j = 0; j < N4 + NL4; j++) anynz |= (y4[j] != 0.0f);
+    for (int j = 0; j < N4; j++) anynz |= (x4[j] != 0.0f);
+    /* exactly silent history: every c_i is exactly 0, the reference keeps its initial (0, 1) */
+    if (!anynz) { *best = 0; *second = 1; return 0; }
+    /* Outside the range where find_best_pitch's own products c^2 y stay finite and normal (c^2 <= ex ytot, 1 <= y <= ytot + 1)
+     * the reference selects on signs alone (underflow) or gets stuck on inf > inf (overflow): parity means reproducing that,
+     * so those streams take the exact path.  Inside the range every score below is a finite, normal quotient. */
+    if (!(ex > 1e-18f) || !(ytot > 1e-18f) || !(ex * ytot * (ytot + 1.0f) < 1e37f)) { st->flag_nonfinite++; return 1; }
+    /* approximate top two by (rounded) score ch^2 / yn (ch > 0): any two distinct lags keep the certificate sound */
     int f1 = -1, f2 = -1;
-    float n1 = 0.f, d1 = 1.f, n2 = 0.f, d2 = 1.f;
+    float r1 = 0.f, r2 = 0.f;
     for (int i = 0; i < NL4; i++) {
         if (!(ch[i] > 0.0f)) continue;
-        float num = ch[i] * ch[i];
-        if (f1 < 0 || num * d1 > n1 * yn[i]) { f2 = f1; n2 = n1; d2 = d1; f1 = i; n1 = num; d1 = yn[i]; }
-        else if (f2 < 0 || num * d2 > n2 * yn[i]) { f2 = i; n2 = num; d2 = yn[i]; }
+        float r = ch[i] * ch[i] / yn[i];
+        if (r > r1) { f2 = f1; r2 = r1; f1 = i; r1 = r; }
+        else if (r > r2) { f2 = i; r2 = r; }
     }
-    if (f1 < 0) {
-        /* no positive approximate value: exact only if every c_i is robustly <= 0, i.e. delta == 0 (all-zero rows) */
-        if (delta == 0.0f) { *best = 0; *second = 1; return 0; }
-        st->flag_sign++; return 1;
-    }
-    if (f2 < 0) { st->flag_sign++; return 1; }
+    if (f1 < 0 || f2 < 0) { st->flag_sign++; return 1; }
     const float a1 = ch[f1] - delta, a2 = ch[f2] - delta;
     if (!(a1 > 0.0f) || !(a2 > 0.0f)) { st->flag_sign++; return 1; }
-    /* tiny scores: products underflow / comparisons degenerate -> exact path */
-    if (!(a2 * a2 > 1e-20f) || !(ch[f1] < 1e18f)) { st->flag_nonfinite++; return 1; }
-    /* T0 = min(lo_F1, lo_F2) as a (num, den) pair */
-    float tn = a1 * a1, td = yn[f1];
-    if (a2 * a2 * td < tn * yn[f2]) { tn = a2 * a2; td = yn[f2]; }
+    if (!(a1 * a1 > 1e-20f) || !(a2 * a2 > 1e-20f)) { st->flag_nonfinite++; return 1; }
+    const float ETA1 = 1.0f + ETA;
+    const float lo1 = a1 * a1 / yn[f1], lo2 = a2 * a2 / yn[f2];
+    const float b1 = ch[f1] + delta, b2 = ch[f2] + delta;
+    const float hi1 = b1 * b1 / yn[f1], hi2 = b2 * b2 / yn[f2];
+    const float t0s = fminf(lo1, lo2);
     int cand[CMAX], nc = 0;
-    float mn = 0.0f, md = 1.0f; /* M = max hi over non-candidates */
+    float hmax = 0.0f; /* M = max hi over non-candidates */
     for (int j = 0; j < NL4; j++) {
         float b = fmaxf(ch[j] + delta, 0.0f);
-        float hn = b * b;
-        int in_c = (j == f1 || j == f2) || (hn * td * (1.0f + ETA) >= tn * yn[j]);
+        float hs = b * b / yn[j];
+        int in_c = (j == f1 || j == f2) || (hs * ETA1 >= t0s);
         if (in_c) {
             if (nc == CMAX) { st->flag_cmax++; return 1; }
             cand[nc++] = j;
-        } else if (hn * md > mn * yn[j]) { mn = hn; md = yn[j]; }
+        } else if (hs > hmax) hmax = hs;
     }
+    const float mbound = hmax * ETA1;
     st->csum += nc;
     if (nc == 2) {
-        /* lo_F1 > hi_F2 (1 + eta) ? */
-        float b2 = ch[f2] + delta;
-        if (a1 * a1 * yn[f2] > b2 * b2 * yn[f1] * (1.0f + ETA)) { *best = f1; *second = f2; return 0; }
+        if (lo1 > hi2 * ETA1) { *best = f1; *second = f2; return 0; }
+        if (lo2 > hi1 * ETA1) { *best = f2; *second = f1; return 0; }
         st->tie12++;
     }
     /* exact values for the candidates, each must beat every non-candidate robustly */
@@ -121,7 +126,7 @@ static int coarse_fast(const float *x4, const float *y4, int *best, int *second,
         for (int j = 0; j < N4; j++) c += x4[j] * y4[cand[k] + j];
         ce[k] = c;
         st->exact_lags++;
-        if (!(c > 0.0f) || !(c * c * md > mn * yn[cand[k]] * (1.0f + ETA))) { st->flag_weakcand++; return 1; }
+        if (!(c > 0.0f) || !(c * c / yn[cand[k]] > mbound * ETA1)) { st->flag_weakcand++; return 1; }
     }
     /* the reference's selection restricted to C (ascending lag; cand[] is ascending) */
     float best_num = -1.0f, second_num = -1.0f, best_den = 0.0f, second_den = 0.0f;
@@ -280,6 +285,9 @@ int main(int argc, char **argv) {
             double gain = 0.05 + 1.5 * urand();
             long roff = nraw ? (long)(urand() * nraw) : 0;
             if (fam == 3) sg = (sidx % 8 == 3) ? 1.0 + 20.0 * urand() : sg * 0.1; /* nearly pure tones: the near-tie stress case */
+            /* amplitude regimes outside the int16 range the reference documents: underflow / overflow of the certificate */
+            static const double scales[8] = {1.0, 1.0, 1.0, 1e4, 3.0, 1e-9, 3e-5, 300.0};
+            const double ascale = scales[(sidx / 4) % 8];
             unsigned long long rs = rng_s;
             float in[FRAME_SIZE], hp[FRAME_SIZE];
             double phase = ph;
@@ -299,12 +307,12 @@ int main(int argc, char **argv) {
                     } else { /* looped speech fixture with gain, plus a little noise */
                         v = nraw ? gain * raw[(roff + nn) % nraw] + 0.02 * sg * nrand() : sg * nrand();
                         /* occasional digital silence */
-                        if (((fr / 13) % 5) == 4) v = 0;
+                        if (((fr / 13) % 5) == 4 || (sidx % 16 == 2 && fr >= 20 && fr < 80)) v = 0;
                     }
                     v = rint(v);
                     if (v > 32767) v = 32767;
                     if (v < -32768) v = -32768;
-                    in[i] = (float)v;
+                    in[i] = (float)(v * ascale);
                 }
                 rs = rng_s;
                 memmove(S->input_mem, S->input_mem + FRAME_SIZE, (PITCH_BUF_SIZE - FRAME_SIZE) * sizeof(float));
@@ -329,7 +337,7 @@ int main(int argc, char **argv) {
                     int pf = remove_doubling_fast(S, PITCH_MAX_PERIOD - is, &gf, &st);
                     if (pf == -1) flagged = 1;
                     else {
-                        if (pf != pe) st.mism_period++;
+                        if (pf != pe) { st.mism_period++; if (st.mism_period < 4) fprintf(stderr, "mismatch stream %d (scale %g fam %d) frame %d: fast %d exact %d\n", sidx, ascale, fam, fr, pf, pe); }
                         if (memcmp(&gf, &ge, 4) != 0) st.mism_gain++;
                     }
                 }

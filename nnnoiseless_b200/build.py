@@ -32,12 +32,13 @@ UNITS = [
     ("pitch.cu", ["-fmad=false"]),
     ("train.cu", ["-fmad=false"]),
     ("spectral.cu", []),
+    ("spectral_warp.cu", []),
     ("rnn.cu", ["-DRNN_RT=256", "-DRNN_UNROLL=8"]),
     ("rnn_mma.cu", []),
     ("frontend.cu", []),
     ("host.cu", []),
 ]
-HEADERS = ["common.cuh", "model.hpp", "audio_io.hpp", os.path.join("..", "..", "include", "rnnoise.h")]
+HEADERS = ["common.cuh", "fft480.cuh", "model.hpp", "audio_io.hpp", os.path.join("..", "..", "include", "rnnoise.h")]
 
 
 def _newer(target, deps):

@@ -56,7 +56,15 @@ struct DeviceTables {
     int16_t bt_lane_start[BT_LANES + 1];
     int16_t bt_band_lane[NB_BANDS + 1];
     int16_t bt_lane_band[BT_LANES];  // band of each lane (lanes of one band are contiguous)
+    // ---- warp-per-stream spectral kernels (spectral_warp.cu) ----
+    float2 twl[15][32];              // exp(-2 pi i b k1 / 480), lane-major: step-2 twiddles of the 32 x 15 FFT
+    // band sums with one warp per stream: the 21 band segments (bins 0..399) are dealt to the 32 lanes, every lane stays
+    // inside ONE segment (segments of <= 16 bins: one lane; 24, 32: two; 48: three; 72, 88: four -- 32 lanes in all)
+    int16_t bp_seg[32];              // segment of lane l (lanes of a segment are contiguous)
+    int16_t bp_b0[32];               // its first bin
+    int16_t bp_n[32];                // its number of bins (<= 22)
 };
+constexpr int BP_MAXBINS = 22;
 
 // One dense or GRU layer as laid out on the device: int8 weights expanded to f32, output dimension padded
 // to a multiple of 4 (np = (nn + 3) & ~3, padding weights/biases are zero) so that a thread can fetch the
@@ -168,10 +176,13 @@ cudaError_t launch_hp_filter(const BatchBuffers& b, const void* in, bool pcm16, 
 // force_exact bit 0: every stream recomputes its coarse search order-exact, bit 1: its sub-harmonic ladder
 // (NNB_PITCH_EXACT=1 sets both: the test reference; 2 / 3 select one of them)
 cudaError_t launch_pitch(const BatchBuffers& b, int slot, int force_exact, cudaStream_t st);
-// spectral.cu
+// spectral.cu (round-1 block-per-stream kernels, NNB_SPECTRAL_V1=1) and spectral_warp.cu (warp-per-stream, default)
 cudaError_t launch_analysis(const BatchBuffers& b, const DeviceTables* tab, int slot, cudaStream_t st);
 cudaError_t launch_synthesis(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride, long sample_stride,
                              float* vad_out, cudaStream_t st);
+cudaError_t launch_analysis_warp(const BatchBuffers& b, const DeviceTables* tab, int slot, cudaStream_t st);
+cudaError_t launch_synthesis_warp(const BatchBuffers& b, const DeviceTables* tab, void* out, bool pcm16, long stream_stride,
+                                  long sample_stride, float* vad_out, cudaStream_t st);
 // rnn.cu
 cudaError_t launch_rnn(const BatchBuffers& b, const DeviceModel& m, const DeviceTables* tab, cudaStream_t st);
 // rnn_mma.cu

@@ -137,6 +137,34 @@ void build_tables(DeviceTables* t) {
             t->bt_lane_start[lane++] = (int16_t)(first + (int)((long)n * l / lanes));
         }
     }
+    // tables of the warp-per-stream spectral kernels
+    for (int k1 = 0; k1 < 15; k1++)
+        for (int b = 0; b < 32; b++) {
+            const double ang = -2.0 * pi * (double)(b * k1) / 480.0;
+            t->twl[k1][b] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+    {
+        int l = 0;
+        for (int sgi = 0; sgi < NB_BANDS - 1; sgi++) {
+            const int first = t->band_start[sgi], size = t->band_start[sgi + 1] - first;
+            const int nl = size <= 16 ? 1 : (size <= 32 ? 2 : (size <= 48 ? 3 : 4));
+            for (int q = 0; q < nl; q++) {
+                const int lo = first + (int)((long)size * q / nl), hi = first + (int)((long)size * (q + 1) / nl);
+                if (l >= 32 || hi - lo > BP_MAXBINS) {
+                    fprintf(stderr, "nnnoiseless_b200: band partition broken\n");
+                    abort();
+                }
+                t->bp_seg[l] = (int16_t)sgi;
+                t->bp_b0[l] = (int16_t)lo;
+                t->bp_n[l] = (int16_t)(hi - lo);
+                l++;
+            }
+        }
+        if (l != 32) {
+            fprintf(stderr, "nnnoiseless_b200: band partition uses %d lanes\n", l);
+            abort();
+        }
+    }
     t->bt_band_lane[NB_BANDS] = (int16_t)lane;
     t->bt_lane_start[lane] = (int16_t)nterm;
     if (lane != BT_LANES || nterm != 800) {
@@ -363,6 +391,7 @@ struct RNNoiseBatch {
     UploadedModel um;
     UploadedMma umm;
     bool rnn_fp32 = false;  // NNB_RNN_FP32=1: CUDA-core FP32 GRU kernel instead of the tensor-core one (debug / comparison)
+    bool spectral_v1 = false;  // NNB_SPECTRAL_V1=1: round-1 block-per-stream analysis / synthesis kernels (comparison)
     bool serial = false;    // NNB_SERIAL=1: all stages on one stream (debug / comparison)
     int pitch_exact = 0;  // NNB_PITCH_EXACT=1: every stream takes the pitch kernel's order-exact recomputation paths (2: coarse only, 3: ladder only)
     unsigned long long frame = 0;  // frames processed so far (ring slot = frame % HIST_SLOTS, set = frame % PIPE_DEPTH)
@@ -468,6 +497,8 @@ int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) 
         b->rnn_fp32 = e1 && e1[0] == '1';
         const char* e2 = getenv("NNB_SERIAL");
         b->serial = e2 && e2[0] == '1';
+        const char* e4 = getenv("NNB_SPECTRAL_V1");
+        b->spectral_v1 = e4 && e4[0] == '1';
         const char* e3 = getenv("NNB_PITCH_EXACT");
         b->pitch_exact = !e3 ? 0 : (e3[0] == '1' ? 3 : (e3[0] == '2' ? 1 : (e3[0] == '3' ? 2 : 0)));
     }
@@ -547,12 +578,18 @@ int launch_stage(RNNoiseBatch* b, int i, const BatchBuffers& v, void* out, const
     switch (i) {
         case 0: CK(launch_hp_filter(v, in, (fmt & kFmtPcmIn) != 0, stream_stride, sample_stride, slot, s)); break;
         case 1: CK(launch_pitch(v, slot, b->pitch_exact, s)); break;
-        case 2: CK(launch_analysis(v, b->d_tab, slot, s)); break;
+        case 2:
+            if (b->spectral_v1) CK(launch_analysis(v, b->d_tab, slot, s));
+            else CK(launch_analysis_warp(v, b->d_tab, slot, s));
+            break;
         case 3:
             if (b->rnn_fp32) CK(launch_rnn(v, b->um.dm, b->d_tab, s));
             else CK(launch_rnn_mma(v, b->umm.dm, b->d_tab, s));
             break;
-        default: CK(launch_synthesis(v, b->d_tab, out, (fmt & kFmtPcmOut) != 0, stream_stride, sample_stride, vad, s)); break;
+        default:
+            if (b->spectral_v1) CK(launch_synthesis(v, b->d_tab, out, (fmt & kFmtPcmOut) != 0, stream_stride, sample_stride, vad, s));
+            else CK(launch_synthesis_warp(v, b->d_tab, out, (fmt & kFmtPcmOut) != 0, stream_stride, sample_stride, vad, s));
+            break;
     }
     return 0;
 }
@@ -912,7 +949,10 @@ int train_step(RNNoiseTrainer* t, float* rows, long row_lane_stride, const float
         switch (i) {
             case 0: CK(launch_train_front(v, t->tb, set, sig, noise, stream_stride, slot, S(i))); break;
             case 1: CK(launch_pitch(v, slot, b->pitch_exact, S(i))); break;
-            case 2: CK(launch_analysis(v, b->d_tab, slot, S(i))); break;
+            case 2:
+                if (b->spectral_v1) CK(launch_analysis(v, b->d_tab, slot, S(i)));
+                else CK(launch_analysis_warp(v, b->d_tab, slot, S(i)));
+                break;
             default: CK(launch_train_rows(v, t->tb, set, rows, row_lane_stride, S(i))); break;
         }
         CK(cudaEventRecord(b->ev[i][e], S(i)));

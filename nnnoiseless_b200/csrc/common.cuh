@@ -63,6 +63,9 @@ struct DeviceTables {
     int16_t bp_seg[32];              // segment of lane l (lanes of a segment are contiguous)
     int16_t bp_b0[32];               // its first bin
     int16_t bp_n[32];                // its number of bins (<= 22)
+    int16_t bp_rot[32];              // rotation of its walk (lane visits bin b0 + (t + rot) mod n): spreads the lanes over the banks
+    int16_t bp_off[32];              // b0 - first bin of the segment
+    float bp_inv[32];                // 1 / (bins of the segment): frac = (off + i) * inv
 };
 constexpr int BP_MAXBINS = 22;
 

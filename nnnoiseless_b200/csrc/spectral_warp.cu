@@ -66,15 +66,18 @@ __device__ __forceinline__ void fft480_warp(float2 (&vx)[15], float2 (&vp)[15], 
 template <int NQ>
 __device__ __forceinline__ void band_sums_warp(const float2* __restrict__ buf, const DeviceTables* __restrict__ tab, float* __restrict__ sc,
                                                int lane, float (&o)[NQ]) {
-    const int sg = tab->bp_seg[lane], b0 = tab->bp_b0[lane], n = tab->bp_n[lane];
+    const int sg = tab->bp_seg[lane], b0 = tab->bp_b0[lane], n = tab->bp_n[lane], rot = tab->bp_rot[lane], off0 = tab->bp_off[lane];
+    const float inv = tab->bp_inv[lane];  // frac = j / size as j * (1 / size): within an ulp of the reference's quotient
     float a[NQ], b[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) a[q] = b[q] = 0.0f;
-#pragma unroll 2
+#pragma unroll
     for (int t = 0; t < BP_MAXBINS; t++) {
         if (t < n) {
-            const int k = b0 + t;
-            const float f = __ldg(&tab->band_frac[k]), g = 1.0f - f;
+            int i = t + rot;  // rotated walk: neighbouring lanes start at different offsets -> different banks
+            if (i >= n) i -= n;
+            const int k = b0 + i;
+            const float f = (float)(off0 + i) * inv, g = 1.0f - f;
             const float2 x = buf[k];
             float e[NQ];
             e[0] = x.x * x.x + x.y * x.y;
@@ -138,7 +141,7 @@ __device__ __forceinline__ void band_sums_warp(const float2* __restrict__ buf, c
 // ================================================================================================
 // K3: analysis -- X, P, band energies, features (src/features.rs:115-219)
 // ================================================================================================
-__global__ void __launch_bounds__(WPB * 32) analysis_warp_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab, int hbase) {
+__global__ void __launch_bounds__(WPB * 32, 6) analysis_warp_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab, int hbase) {
     __shared__ __align__(16) float2 sbuf[WPB][WBUF];
     __shared__ float ssc[WPB][WSC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(WPB * 32) analysis_warp_kernel(BatchBuffers bb
 __device__ __forceinline__ short to_pcm16w(float v) { return (short)roundf(fminf(fmaxf(v, -32768.0f), 32767.0f)); }
 
 template <typename TOut>
-__global__ void __launch_bounds__(WPB * 32) synthesis_warp_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab,
+__global__ void __launch_bounds__(WPB * 32, 5) synthesis_warp_kernel(BatchBuffers bb, const DeviceTables* __restrict__ tab,
                                                                   TOut* __restrict__ out, long stream_stride, long sample_stride,
                                                                   float* __restrict__ vad_out) {
     __shared__ __align__(16) float2 sbuf[WPB][WBUF];

@@ -35,6 +35,7 @@ UNITS = [
     ("spectral_warp.cu", []),
     ("rnn.cu", ["-DRNN_RT=256", "-DRNN_UNROLL=8"]),
     ("rnn_mma.cu", []),
+    ("rnn_tc.cu", []),
     ("frontend.cu", []),
     ("host.cu", []),
 ]

@@ -191,6 +191,40 @@ cudaError_t launch_rnn(const BatchBuffers& b, const DeviceModel& m, const Device
 // rnn_mma.cu
 cudaError_t launch_rnn_mma(const BatchBuffers& b, const DeviceModelMma& m, const DeviceTables* tab, cudaStream_t st);
 
+// rnn_tc.cu: tcgen05 / TMEM formulation
+// ---- model image for this kernel (built on the host, one bulk copy per CTA) ----
+constexpr int TC_PHASES = 9;
+enum { PH_DENSE = 0, PH_VAD_ZR, PH_VAD_H, PH_VAD_OUT, PH_NOISE_ZR, PH_NOISE_H, PH_DEN_ZR, PH_DEN_H, PH_OUT };
+struct TcPhase {
+    int n;            // MMA N (multiple of 16)
+    int nk;           // K chunks of 16 activations
+    int d_col;        // accumulator column inside the D region
+    uint32_t w_off;   // byte offset of the [n][16 nk] weight operand in the blob
+    uint32_t b_off;   // byte offset of the n f32 biases
+    short chunk[16];  // >= 0: TMEM activation chunk (16 halves); < 0: shared-memory feature chunk -(f + 1)
+};
+struct DeviceModelTc {
+    TcPhase ph[TC_PHASES];
+    int nd, nv, nn, ndn;                                   // neurons of dense / vad / noise / denoise
+    int p_d, p_v, p_n, p_dn;                               // the same padded to multiples of 8
+    int o_dense, o_vad, o_noise, o_den, o_rh;              // activation offsets in halves (multiples of 8)
+    int act_dense, act_vad, act_noise, act_den, act_out, act_vadout;
+    int state_size;
+    const unsigned char* blob;                             // weights | biases | tanh table, in device memory
+    uint32_t blob_bytes, table_off;
+};
+
+struct UploadedTc {
+    DeviceModelTc dm{};
+    unsigned char* d_blob = nullptr;
+    size_t smem_bytes = 0;
+    bool ok = false;
+};
+
+struct HostModel;
+int upload_model_tc(const HostModel& hm, UploadedTc* u, cudaStream_t st);   // 0 ok (u->ok tells whether the model fits), < 0 CUDA error
+cudaError_t launch_rnn_tc(const BatchBuffers& b, const UploadedTc& u, cudaStream_t st);
+
 // train.cu (-fmad=false)
 cudaError_t launch_train_front(const BatchBuffers& b, const TrainBuffers& tb, int set, const float* signal, const float* noise,
                                long stream_stride, int slot, cudaStream_t st);

@@ -61,7 +61,9 @@ namespace {
     } while (0)
 
 // ---- tables (src/lib.rs:99-136, src/util.rs:3-27) -------------------------------------------------
-const float kTansig[201] = {
+}  // namespace
+namespace nnb {
+extern const float kTansigTable[201] = {
     0.000000f, 0.039979f, 0.079830f, 0.119427f, 0.158649f, 0.197375f, 0.235496f, 0.272905f, 0.309507f, 0.345214f, 0.379949f,
     0.413644f, 0.446244f, 0.477700f, 0.507977f, 0.537050f, 0.564900f, 0.591519f, 0.616909f, 0.641077f, 0.664037f, 0.685809f,
     0.706419f, 0.725897f, 0.744277f, 0.761594f, 0.777888f, 0.793199f, 0.807569f, 0.821040f, 0.833655f, 0.845456f, 0.856485f,
@@ -82,6 +84,8 @@ const float kTansig[201] = {
     0.999999f, 0.999999f, 0.999999f, 1.000000f, 1.000000f, 1.000000f, 1.000000f, 1.000000f, 1.000000f, 1.000000f, 1.000000f,
     1.000000f, 1.000000f, 1.000000f,
 };
+}  // namespace nnb
+namespace {
 const int kEband5ms[NB_BANDS] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 34, 40, 48, 60, 78, 100};
 
 void build_tables(DeviceTables* t) {
@@ -102,7 +106,7 @@ void build_tables(DeviceTables* t) {
             if (j == 0) v *= std::sqrt(0.5f);
             t->dct[i * NB_BANDS + j] = v;
         }
-    for (int i = 0; i < 201; i++) t->tansig[i] = kTansig[i];
+    for (int i = 0; i < 201; i++) t->tansig[i] = kTansigTable[i];
     for (int k = 0; k < 480; k++)
         t->tw480[k] = make_float2((float)std::cos(-2.0 * pi * (double)k / 480.0), (float)std::sin(-2.0 * pi * (double)k / 480.0));
     for (int k = 0; k <= 480; k++)
@@ -396,6 +400,8 @@ struct RNNoiseBatch {
     DeviceTables* d_tab = nullptr;
     UploadedModel um;
     UploadedMma umm;
+    UploadedTc utc;         // tcgen05 / TMEM formulation (default when the model fits its budget)
+    bool rnn_mma = false;   // NNB_RNN_MMA=1: the mma.sync kernel of round 1 (comparison; also the fallback for large models)
     bool rnn_fp32 = false;  // NNB_RNN_FP32=1: CUDA-core FP32 GRU kernel instead of the tensor-core one (debug / comparison)
     bool spectral_v1 = false;  // NNB_SPECTRAL_V1=1: round-1 block-per-stream analysis / synthesis kernels (comparison)
     bool serial = false;    // NNB_SERIAL=1: all stages on one stream (debug / comparison)
@@ -498,11 +504,15 @@ int batch_init(RNNoiseBatch* b, const HostModel& hm, int n_streams, int device) 
     b->allocs.push_back(b->um.d_blob);
     if (upload_model_mma(hm, &b->umm, b->st[0])) return -1;
     b->allocs.push_back(b->umm.d_blob);
+    if (upload_model_tc(hm, &b->utc, b->st[0])) return fail("tensor-core model upload");
+    if (b->utc.d_blob) b->allocs.push_back(b->utc.d_blob);
     {
         const char* e1 = getenv("NNB_RNN_FP32");
         b->rnn_fp32 = e1 && e1[0] == '1';
         const char* e2 = getenv("NNB_SERIAL");
         b->serial = e2 && e2[0] == '1';
+        const char* e5 = getenv("NNB_RNN_MMA");
+        b->rnn_mma = e5 && e5[0] == '1';
         const char* e4 = getenv("NNB_SPECTRAL_V1");
         b->spectral_v1 = e4 && e4[0] == '1';
         const char* e3 = getenv("NNB_PITCH_EXACT");
@@ -590,6 +600,7 @@ int launch_stage(RNNoiseBatch* b, int i, const BatchBuffers& v, void* out, const
             break;
         case 3:
             if (b->rnn_fp32) CK(launch_rnn(v, b->um.dm, b->d_tab, s));
+            else if (b->utc.ok && !b->rnn_mma) CK(launch_rnn_tc(v, b->utc, s));
             else CK(launch_rnn_mma(v, b->umm.dm, b->d_tab, s));
             break;
         default:

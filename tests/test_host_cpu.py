@@ -138,3 +138,16 @@ def test_model_parser_fuzz_agrees_with_oracle(builtin_bytes):
             assert ours.to_bytes() == b
 
     check()
+
+
+def test_tcgen05_weight_packing_selftest(builtin_bytes, sh_bytes):
+    """The tcgen05 GRU kernel's model image (K-major UMMA operands per layer phase, activation-chunk lists, biases) replayed
+    on the host in plain f32 equals a direct evaluation of src/rnn.rs:343-379 from the model bytes -- the packing logic is
+    checked without a GPU (the instruction / TMEM layouts themselves: tools/probes/tcgen05_probe.cu on the GPU)."""
+    L = nb.lib()
+    L.nnb_tc_pack_selftest.restype = C.c_double
+    L.nnb_tc_pack_selftest.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
+    for model in (builtin_bytes, sh_bytes):
+        for seed in range(8):
+            assert 0.0 <= L.nnb_tc_pack_selftest(model, len(model), seed) < 2e-5
+    assert L.nnb_tc_pack_selftest(builtin_bytes[:-1], len(builtin_bytes) - 1, 0) == -1.0

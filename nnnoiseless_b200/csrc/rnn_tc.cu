@@ -37,7 +37,8 @@ extern const float kTansigTable[201];  // host.cu (src/util.rs:3-27)
 namespace {
 
 constexpr int TM = 128;           // streams per tile = MMA M
-constexpr int NT = 256;           // threads: 8 warps, two per TMEM lane quarter
+constexpr int NT = 512;           // threads: 16 warps, four per TMEM lane quarter (a warp reaches only lanes 32 (w % 4) ..)
+constexpr int NCH = NT / 128;     // column slices: which groups of 8 neurons a thread takes
 constexpr int A_HI = 0, A_LO = 144, D_OFF = 288;  // TMEM columns
 constexpr int A_MAX_HALVES = 288; // 18 K-chunks of 16
 constexpr int D_COLS = 192;
@@ -107,9 +108,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+// tcgen05.ld is asynchronous: registers are valid only after this wait (several loads may share one).  The empty
+// volatile asm statements with "+" operands pin every use of the loaded registers behind the wait.
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void after_wait(float (&v)[8]) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
+}
+__device__ __forceinline__ void after_wait(uint32_t (&v)[4]) { asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3])::"memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(__float_as_uint(v[0])),
@@ -144,6 +154,21 @@ struct Row {
     __device__ __forceinline__ uint32_t d(int col) const { return tm + D_OFF + col; }
     __device__ __forceinline__ uint32_t ahi(int half_off) const { return tm + A_HI + (half_off >> 1); }
     __device__ __forceinline__ uint32_t alo(int half_off) const { return tm + A_LO + (half_off >> 1); }
+    // read eight activations back as hi + lo (what the tensor core multiplies: ~22 significant bits of the f32 value):
+    // issue the two loads, and after tmem_wait_ld() combine them
+    __device__ __forceinline__ void get_act_issue(int half_off, uint32_t (&hi)[4], uint32_t (&lo)[4]) const {
+        tmem_ld4(ahi(half_off), hi);
+        tmem_ld4(alo(half_off), lo);
+    }
+    __device__ __forceinline__ static void get_act_finish(uint32_t (&hi)[4], uint32_t (&lo)[4], float (&v)[8]) {
+        after_wait(hi);
+        after_wait(lo);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            v[2 * i] = __half2float(__ushort_as_half((unsigned short)(hi[i] & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(lo[i] & 0xffffu)));
+            v[2 * i + 1] = __half2float(__ushort_as_half((unsigned short)(hi[i] >> 16))) + __half2float(__ushort_as_half((unsigned short)(lo[i] >> 16)));
+        }
+    }
     // write eight activations (columns half_off .. half_off + 7 of the A operand) as hi / lo halves
     __device__ __forceinline__ void put_act(int half_off, const float (&v)[8]) const {
         uint32_t hi[4], lo[4];
@@ -163,7 +188,7 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
     const float* table = reinterpret_cast<const float*>(wblob + m.table_off);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = warp & 3, ch = warp >> 2;
+    const int q = warp & 3, ch = warp >> 2;  // lane quarter, column slice
     const int row = 32 * q + lane;
 
     if (tid == 0) {
@@ -196,6 +221,7 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
     uint32_t par = 0;  // parity of bars[0]
     const int SS = m.state_size;
     const int so_n = m.nv, so_d = m.nv + m.nn;  // state offsets in HBM (vad | noise | denoise)
+    const bool vec_ok = ((m.nv | m.nn | m.ndn) & 3) == 0;
 
     // one phase: elected thread issues the MMAs (hi and lo halves of every K chunk against the same weights) and
     // commits them; everybody waits for the accumulators
@@ -244,9 +270,7 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
         float* hsrc = bb.gru_state + (size_t)(live ? s : 0) * SS;
 
         // ---- features -> shared-memory A operand (6 groups of 8 columns; this thread takes 3), states -> TMEM ----
-#pragma unroll
-        for (int gi = 0; gi < 3; gi++) {
-            const int g = 2 * gi + ch;
+        for (int g = ch; g < 2 * FEAT_CHUNKS; g += NCH) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
@@ -262,10 +286,16 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
             *reinterpret_cast<uint4*>(featA + (2 * FEAT_CHUNKS + g) * FEAT_GROUP_BYTES + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         auto load_state = [&](int nn_, int p8, int s_off, int a_off) {
-            for (int g = ch; g < p8 / 8; g += 2) {
+            for (int g = ch; g < p8 / 8; g += NCH) {
                 float v[8];
+                if (live && 8 * g + 8 <= nn_ && vec_ok) {  // rows are 16-byte aligned when every layer width is a multiple of 4
+                    const float4 t0 = __ldg(reinterpret_cast<const float4*>(hsrc + s_off + 8 * g));
+                    const float4 t1 = __ldg(reinterpret_cast<const float4*>(hsrc + s_off + 8 * g + 4));
+                    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+                } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = (live && 8 * g + i < nn_) ? __ldg(hsrc + s_off + 8 * g + i) : 0.0f;
+                    for (int i = 0; i < 8; i++) v[i] = (live && 8 * g + i < nn_) ? __ldg(hsrc + s_off + 8 * g + i) : 0.0f;
+                }
                 R.put_act(a_off + 8 * g, v);
             }
         };
@@ -277,9 +307,11 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
         run_phase(PH_DENSE, PH_DENSE);
         {
             const float* bias = reinterpret_cast<const float*>(wblob + m.ph[PH_DENSE].b_off);
-            for (int g = ch; g < m.p_d / 8; g += 2) {
+            for (int g = ch; g < m.p_d / 8; g += NCH) {
                 float a[8];
                 tmem_ld8(R.d(m.ph[PH_DENSE].d_col + 8 * g), a);
+                tmem_wait_ld();
+                after_wait(a);
 #pragma unroll
                 for (int i = 0; i < 8; i++) a[i] = (8 * g + i < m.nd) ? activate(m.act_dense, WEIGHTS_SCALE * (a[i] + bias[8 * g + i]), table) : 0.0f;
                 R.put_act(m.o_dense + 8 * g, a);
@@ -292,14 +324,20 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
             {
                 const float* bias = reinterpret_cast<const float*>(wblob + m.ph[pzr].b_off);
                 const int dz = m.ph[pzr].d_col;
-                for (int g = ch; g < p8 / 8; g += 2) {
-                    float z[8], r[8];
+                for (int g = ch; g < p8 / 8; g += NCH) {
+                    float z[8], r[8], hpv[8];
+                    uint32_t thi[4], tlo[4];
                     tmem_ld8(R.d(dz + 8 * g), z);
                     tmem_ld8(R.d(dz + p8 + 8 * g), r);
+                    R.get_act_issue(a_off + 8 * g, thi, tlo);  // previous state as the tensor core sees it (hi + lo)
+                    tmem_wait_ld();
+                    after_wait(z);
+                    after_wait(r);
+                    Row::get_act_finish(thi, tlo, hpv);
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int o = 8 * g + i;
-                        const float hp = (live && o < nn_) ? hsrc[s_off + o] : 0.0f;
+                        const float hp = hpv[i];
                         z[i] = sigmoid_approx(WEIGHTS_SCALE * (z[i] + bias[o]), table);
                         r[i] = (o < nn_) ? sigmoid_approx(WEIGHTS_SCALE * (r[i] + bias[p8 + o]), table) * hp : 0.0f;  // reset gate scales the previous state
                     }
@@ -311,17 +349,31 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
             {
                 const float* bias = reinterpret_cast<const float*>(wblob + m.ph[phh].b_off);
                 const int dz = m.ph[pzr].d_col, dh = m.ph[phh].d_col;
-                for (int g = ch; g < p8 / 8; g += 2) {
-                    float z[8], hh[8];
+                for (int g = ch; g < p8 / 8; g += NCH) {
+                    float z[8], hh[8], hpv[8];
+                    uint32_t thi[4], tlo[4];
                     tmem_ld8(R.d(dz + 8 * g), z);
                     tmem_ld8(R.d(dh + 8 * g), hh);
+                    R.get_act_issue(a_off + 8 * g, thi, tlo);
+                    tmem_wait_ld();
+                    after_wait(z);
+                    after_wait(hh);
+                    Row::get_act_finish(thi, tlo, hpv);
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int o = 8 * g + i;
-                        const float hp = (live && o < nn_) ? hsrc[s_off + o] : 0.0f;
                         const float c = activate(act, WEIGHTS_SCALE * (hh[i] + bias[o]), table);
-                        hh[i] = (o < nn_) ? z[i] * hp + (1.0f - z[i]) * c : 0.0f;
-                        if (upd && o < nn_) hsrc[s_off + o] = hh[i];
+                        hh[i] = (o < nn_) ? z[i] * hpv[i] + (1.0f - z[i]) * c : 0.0f;
+                    }
+                    if (upd) {
+                        if (8 * g + 8 <= nn_ && vec_ok) {
+                            *reinterpret_cast<float4*>(hsrc + s_off + 8 * g) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                            *reinterpret_cast<float4*>(hsrc + s_off + 8 * g + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                if (8 * g + i < nn_) hsrc[s_off + 8 * g + i] = hh[i];
+                        }
                     }
                     R.put_act(a_off + 8 * g, hh);
                 }
@@ -334,6 +386,8 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
         if (ch == 0) {
             float a[8];
             tmem_ld8(R.d(m.ph[PH_VAD_OUT].d_col), a);
+            tmem_wait_ld();
+            after_wait(a);
             const float* bias = reinterpret_cast<const float*>(wblob + m.ph[PH_VAD_OUT].b_off);
             if (upd) bb.vad[s] = activate(m.act_vadout, WEIGHTS_SCALE * (a[0] + bias[0]), table);
         }
@@ -343,9 +397,11 @@ __global__ void __launch_bounds__(NT, 1) rnn_tc_kernel(BatchBuffers bb, DeviceMo
         run_phase(PH_OUT, PH_OUT);
         {
             const float* bias = reinterpret_cast<const float*>(wblob + m.ph[PH_OUT].b_off);
-            for (int g = ch; g < (NB_BANDS + 7) / 8; g += 2) {
+            for (int g = ch; g < (NB_BANDS + 7) / 8; g += NCH) {
                 float a[8];
                 tmem_ld8(R.d(m.ph[PH_OUT].d_col + 8 * g), a);
+                tmem_wait_ld();
+                after_wait(a);
                 if (upd) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) {

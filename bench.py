@@ -325,6 +325,11 @@ def run_reference(args):
 
 def run_b200(args):
     cpus0 = all_cpus()
+    # stdout carries exactly ONE JSON line: whatever libraries print on the way (e.g. the NCCL version banner, written by
+    # C code straight to fd 1) is diverted to stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import nnnoiseless_b200 as nb
@@ -562,7 +567,10 @@ def run_b200(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "legacy_abi": legacy,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -29,12 +29,17 @@
 // (stream, lag-group) lane-tasks with register sliding windows, or one warp per stream with the 480 samples
 // dealt to the lanes (15 each: conflict-free scalar reads for arbitrary lags, x held in registers).
 //
-// Shared-memory tile (dynamic, SB = 16 streams per block -> ~111 KB, two blocks per SM):
+// Shared-memory tile (dynamic, SB = 16 streams per block -> 73 KB, THREE blocks per SM: the serial phases of one block
+// hide behind the dense phases of two others):
 //   P   [SB][868]  2x-decimated, LPC-whitened history (pitch_buf); row stride 868 = 16B aligned and
-//                  = 4 (mod 32) so that lane-per-stream float4 reads are bank-conflict free
-//   Y4  [SB][436]  its even samples (the 4x-decimated signal); later reused for yy_lookup [SB][387]
-//   XC  [SB][149]  coarse cross-correlation      YN4 [SB][149]  coarse running energy (exact)
-//   CK  [SB][39]   fine running energy, one checkpoint every 8 lags (replayed where the fine search needs it)
+//                  = 4 (mod 32) so that lane-per-stream float4 reads are bank-conflict free.  The 4x-decimated
+//                  signal of the coarse search is P at stride 2 (no second copy: it cost 28 KB and the third block)
+//   XC  [SB][149]  coarse cross-correlation; dead after the coarse search, then: IPR | LAGS | NLAG | YYS | YYK
+//   YNK [SB][75]   coarse running energy (exact), every second lag (the odd lags are one replayed step away)
+//   CK  [SB][39]   fine running energy, one checkpoint every 8 lags
+//   YYK [SB][25]   yy_lookup, one checkpoint every 16 lags; YYS [SB][24] its values at the lags the ladder reads
+// All three running energies are sequential recurrences; a replay from a checkpoint repeats the same operations in the
+// same order, hence the same bits.
 #include <atomic>
 
 #include "common.cuh"
@@ -68,9 +73,9 @@ constexpr int HALF_N = PITCH_FRAME_SIZE / 2;                           // 480
 constexpr int MIN_PERIOD2 = PITCH_MIN_PERIOD / 2;                      // 30
 
 constexpr int P_LD = 868;
-constexpr int Y4_LD = 436;
 constexpr int XC_LD = 149;
-constexpr int YY_LD = 387;
+constexpr int YNK_LD = 75;   // checkpoints of the coarse running energy (every second lag: 74 values)
+constexpr int YYK_STEP = 16;
 constexpr int IPR_LD = 31;
 constexpr int FX_LD = 17;  // two aligned 8-lag fine windows per stream
 constexpr int NGRP = (NL4 + 3) / 4;  // 37 lag groups of 4
@@ -83,39 +88,39 @@ constexpr float KAPPA4 = 3.1e-5f;
 constexpr float KAPPA2 = 6.0e-5f;
 constexpr float ETA1 = 1.00001f;     // slack of every certified comparison (covers the float roundings of the check itself)
 
-constexpr int OFF_P = 0;
-constexpr int OFF_Y4 = OFF_P + SB * P_LD;
-constexpr int OFF_XC = OFF_Y4 + SB * Y4_LD;
-constexpr int OFF_YN4 = OFF_XC + SB * XC_LD;
-constexpr int OFF_AC = OFF_YN4 + SB * XC_LD;     // [5][SB]
-constexpr int OFF_LPC = OFF_AC + 5 * SB;         // [5][SB]
-constexpr int OFF_XX = OFF_LPC + 5 * SB;         // [SB]
-constexpr int OFF_BND = OFF_XX + SB;             // [3][SB]: sum x_lp4^2 | sum P[0..384)^2 | sum Y4[0..192)^2
-constexpr int OFF_NZ = OFF_BND + 3 * SB;         // int [2][SB]: OR of the magnitude bits of P[384..864) | P[0..384)
-constexpr int OFF_IPR = OFF_NZ + 2 * SB;         // [SB][31]
-constexpr int OFF_FX = OFF_IPR + SB * IPR_LD;    // [SB][17]
-constexpr int OFF_SI = OFF_FX + SB * FX_LD;      // int [5][SB]: best4, second4, t0, t, t1b
-constexpr int OFF_CTR = OFF_SI + 5 * SB;         // int [8]
-constexpr int OFF_LAGS = OFF_CTR + 8;            // int [SB][24]
-constexpr int OFF_NLAG = OFF_LAGS + SB * LAG_LD; // int [SB]
-constexpr int OFF_FLAG = OFF_NLAG + SB;          // int [SB]: bit 0 coarse all-exact, bit 1 remove_doubling all-exact, bit 2 coarse resolved
-constexpr int OFF_CXL = OFF_FLAG + SB;           // int [SB]: streams whose coarse search is recomputed exactly
-constexpr int OFF_RXL = OFF_CXL + SB;            // int [SB]: streams whose ladder is recomputed exactly
 constexpr int CK_STEP = 8;                         // fine running energy: one checkpoint every 8 lags
 constexpr int CK_N = (NL2 + CK_STEP - 1) / CK_STEP;  // 37
 constexpr int CK_LD = 39;
-constexpr int OFF_CK = OFF_RXL + SB;               // [SB][39]
-constexpr int SMEM_FLOATS = OFF_CK + SB * CK_LD;
-// scratch of the coarse selection, alive only before FX / IPR are first written: aliased onto them
-constexpr int OFF_CAND = OFF_IPR;                  // int [SB][CMAX]
-constexpr int OFF_CEX = OFF_CAND + SB * CMAX;      // [SB][CMAX]
-constexpr int OFF_XT = OFF_CEX + SB * CMAX;        // int [SB * CMAX]
-constexpr int OFF_MB = OFF_XT + SB * CMAX;         // [SB]: upper bound of every non-candidate score
-constexpr int OFF_NEEDX = OFF_MB + SB;             // int [SB]
-static_assert(OFF_NEEDX + SB <= OFF_SI, "selection scratch must fit in the IPR + FX region");
+constexpr int SF_LD = 19;                          // selection scratch (CAND 8 | CEX 8 | MB | NEEDX), then FX[17]
+constexpr int OFF_P = 0;
+constexpr int OFF_XC = OFF_P + SB * P_LD;
+constexpr int OFF_YNK = OFF_XC + SB * XC_LD;
+constexpr int OFF_CK = OFF_YNK + SB * YNK_LD;      // [SB][39]
+constexpr int OFF_SF = OFF_CK + SB * CK_LD;        // [SB][26]
+constexpr int OFF_AC = OFF_SF + SB * SF_LD;        // [5][SB]
+constexpr int OFF_LPC = OFF_AC + 5 * SB;           // [5][SB]
+constexpr int OFF_XX = OFF_LPC + 5 * SB;           // [SB]
+constexpr int OFF_BND = OFF_XX + SB;               // [3][SB]: sum x_lp4^2 | sum P[0..384)^2 | sum of the even P[0..384)^2
+constexpr int OFF_NZ = OFF_BND + 3 * SB;           // int [2][SB]: OR of the magnitude bits of P[384..864) | P[0..384)
+constexpr int OFF_SI = OFF_NZ + 2 * SB;            // int [6][SB]: best4, second4, t0, t, t1b, position of t in LAGS
+constexpr int OFF_CTR = OFF_SI + 6 * SB;           // int [8]
+constexpr int OFF_FLAG = OFF_CTR + 8;              // int [SB]: bit 0 coarse all-exact, bit 1 remove_doubling all-exact, bit 2 coarse resolved
+constexpr int OFF_CXL = OFF_FLAG + SB;             // int [SB]: streams whose coarse search is recomputed exactly
+constexpr int OFF_RXL = OFF_CXL + SB;              // int [SB]: streams whose ladder is recomputed exactly
+constexpr int OFF_XTL = OFF_RXL + SB;             // int [SB * CMAX]: exact single-lag tasks of the coarse search
+constexpr int SMEM_FLOATS = OFF_XTL + SB * CMAX;
+// inside a stream's XC row once the coarse search is over (all offsets in floats):
+constexpr int XO_IPR = 0;                          // [31]
+constexpr int XO_LAGS = 32;                        // int [24]
+constexpr int XO_NLAG = 56;                        // int
+constexpr int XO_YYS = 57;                         // [24]  yy_lookup at the lags of LAGS
+constexpr int XO_YYK = 81;                         // [25]  yy_lookup checkpoints (lag 16 m)
+static_assert(XO_YYK + HALF_MAX / YYK_STEP + 1 <= XC_LD, "ladder scratch must fit in the XC row");
+// inside a stream's SF row
+constexpr int SO_CAND = 0, SO_CEX = CMAX, SO_MB = 2 * CMAX, SO_NEEDX = 2 * CMAX + 1;
 static_assert(CK_N <= CK_LD, "checkpoint row too short");
-static_assert(YY_LD <= Y4_LD, "yy must fit in the Y4 region");
-static_assert(2 * (SMEM_FLOATS * 4 + 1024) <= 228 * 1024, "two blocks per SM");
+static_assert(FX_LD <= SF_LD && SO_NEEDX < SF_LD, "fine-window results reuse the selection scratch");
+static_assert(3 * (SMEM_FLOATS * 4 + 1024) <= 228 * 1024, "three blocks per SM");
 
 
 __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
@@ -255,26 +260,28 @@ __device__ __forceinline__ void inner_prod_window4_aligned(const float4* __restr
     for (int c = 0; c < 4; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
 }
 
-// Sixteen consecutive coarse lags 16g..16g+15 of one stream, FMA (certified afterwards): one x and one y LDS.128 per 64
-// multiply-adds -- shared memory bandwidth, not the FP pipe, was the limit of the 4-lag version.
-__device__ __forceinline__ void coarse_group16(const float* __restrict__ y4row, int g, float* __restrict__ xcrow) {
-    const float4* xr = reinterpret_cast<const float4*>(y4row + HALF_MAX / 2);
-    const float4* yr = reinterpret_cast<const float4*>(y4row + 16 * g);
+// Sixteen consecutive coarse lags 16g..16g+15 of one stream, FMA (certified afterwards).  The 4x-decimated operands are the
+// even samples of the whitened row: x_lp4[j] = p[384 + 2 j], y_lp4[j] = p[2 j] (src/pitch.rs:74-79), two per LDS.128.
+// Four LDS.128 per 64 multiply-adds.
+__device__ __forceinline__ void coarse_group16(const float* __restrict__ prow, int g, float* __restrict__ xcrow) {
+    const float4* xr = reinterpret_cast<const float4*>(prow + HALF_MAX);
+    const float4* yr = reinterpret_cast<const float4*>(prow + 32 * g);
     float acc[16];
 #pragma unroll
     for (int c = 0; c < 16; c++) acc[c] = 0.0f;
     float e[20];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 8; q++) {
         const float4 v = yr[q];
-        e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w;
+        e[2 * q] = v.x;
+        e[2 * q + 1] = v.z;
     }
-#pragma unroll 5  // the 20-float window rotates with period 5: no register moves at the back-edge
+#pragma unroll 5  // the 20-sample window rotates with period 5: no register moves at the back-edge
     for (int m = 0; m < N4 / 4; m++) {
-        const float4 x = xr[m];
-        const float4 v = yr[m + 4];
-        e[16] = v.x; e[17] = v.y; e[18] = v.z; e[19] = v.w;
-        const float xv[4] = {x.x, x.y, x.z, x.w};
+        const float4 xa = xr[2 * m], xb = xr[2 * m + 1];
+        const float4 va = yr[2 * m + 8], vb = yr[2 * m + 9];
+        e[16] = va.x; e[17] = va.z; e[18] = vb.x; e[19] = vb.z;
+        const float xv[4] = {xa.x, xa.z, xb.x, xb.z};
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
@@ -287,36 +294,33 @@ __device__ __forceinline__ void coarse_group16(const float* __restrict__ y4row, 
         if (16 * g + c < NL4) xcrow[16 * g + c] = acc[c];
 }
 
-// Four consecutive coarse lags 4g..4g+3 of one stream (src/pitch.rs:82, 296-363): every accumulator sums
-// x_lp4[j] * y_lp4[lag + j] with j ascending, operands via a sliding register window (one LDS.128 per 16 MACs).
-// EXACT: separate multiply and add in the reference's order.  !EXACT: fused, certified afterwards.
-template <bool EXACT>
-__device__ __forceinline__ void coarse_group(const float* __restrict__ y4row, int g, float* __restrict__ xcrow) {
-    const float4* xr = reinterpret_cast<const float4*>(y4row + HALF_MAX / 2);
-    const float4* yr = reinterpret_cast<const float4*>(y4row + 4 * g);
+// Four consecutive coarse lags 4g..4g+3 of one stream in the REFERENCE's order (src/pitch.rs:82, 296-363): every accumulator
+// sums x_lp4[j] * y_lp4[lag + j] with j ascending, separate multiply and add.  Used where the certificate of the FMA
+// values fails.
+__device__ __forceinline__ void coarse_group4_exact(const float* __restrict__ prow, int g, float* __restrict__ xcrow) {
+    const float4* xr = reinterpret_cast<const float4*>(prow + HALF_MAX);
+    const float4* yr = reinterpret_cast<const float4*>(prow + 8 * g);
     float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
-    float4 w = yr[0];
+    float e[8];
+    {
+        const float4 v0 = yr[0], v1 = yr[1];
+        e[0] = v0.x; e[1] = v0.z; e[2] = v1.x; e[3] = v1.z;
+    }
 #pragma unroll 2
     for (int m = 0; m < N4 / 4; m++) {
-        const float4 x = xr[m];
-        const float4 wn = yr[m + 1];
-        const float e[8] = {w.x, w.y, w.z, w.w, wn.x, wn.y, wn.z, wn.w};
-        const float xv[4] = {x.x, x.y, x.z, x.w};
+        const float4 xa = xr[2 * m], xb = xr[2 * m + 1];
+        const float4 va = yr[2 * m + 2], vb = yr[2 * m + 3];
+        e[4] = va.x; e[5] = va.z; e[6] = vb.x; e[7] = vb.z;
+        const float xv[4] = {xa.x, xa.z, xb.x, xb.z};
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            if (EXACT) {
-                c0 = fa(c0, fm(xv[u], e[u]));
-                c1 = fa(c1, fm(xv[u], e[u + 1]));
-                c2 = fa(c2, fm(xv[u], e[u + 2]));
-                c3 = fa(c3, fm(xv[u], e[u + 3]));
-            } else {
-                c0 = ffma(xv[u], e[u], c0);
-                c1 = ffma(xv[u], e[u + 1], c1);
-                c2 = ffma(xv[u], e[u + 2], c2);
-                c3 = ffma(xv[u], e[u + 3], c3);
-            }
+            c0 = fa(c0, fm(xv[u], e[u]));
+            c1 = fa(c1, fm(xv[u], e[u + 1]));
+            c2 = fa(c2, fm(xv[u], e[u + 2]));
+            c3 = fa(c3, fm(xv[u], e[u + 3]));
         }
-        w = wn;
+#pragma unroll
+        for (int q = 0; q < 4; q++) e[q] = e[q + 4];
     }
     float* o = xcrow + 4 * g;
     o[0] = c0;
@@ -341,37 +345,48 @@ __device__ unsigned long long g_pitch_prof[16];
 
 // stats[0] += streams whose coarse search was recomputed exactly, stats[1] += streams whose ladder was,
 // stats[2] += streams processed (one atomic per block each)
-__global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ hist, int32_t* __restrict__ last_period,
+__global__ void __launch_bounds__(NT, 3) pitch_kernel(const float* __restrict__ hist, int32_t* __restrict__ last_period,
                                                       float* __restrict__ last_gain, int32_t* __restrict__ pitch_out,
                                                       int n_streams, int hbase, int force_exact,
                                                       unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) float sm[];
     float* P = sm + OFF_P;
-    float* Y4 = sm + OFF_Y4;
     float* XC = sm + OFF_XC;
-    float* YN4 = sm + OFF_YN4;
+    float* YNK = sm + OFF_YNK;
+    float* CK = sm + OFF_CK;
+    float* SF = sm + OFF_SF;
     float* AC = sm + OFF_AC;
     float* LPC = sm + OFF_LPC;
     float* XX = sm + OFF_XX;
     float* BND = sm + OFF_BND;
     int* NZ = reinterpret_cast<int*>(sm + OFF_NZ);
-    float* IPR = sm + OFF_IPR;
-    float* FX = sm + OFF_FX;
     int* SI = reinterpret_cast<int*>(sm + OFF_SI);
     int* CTR = reinterpret_cast<int*>(sm + OFF_CTR);
-    // CTR: [0] coarse lane-task counter, [1] remove_doubling stream counter, [2] streams in CXL, [3] entries in XT,
-    //      [4] streams in RXL, [7] CXL entries already recomputed
-    int* LAGS = reinterpret_cast<int*>(sm + OFF_LAGS);
-    int* NLAG = reinterpret_cast<int*>(sm + OFF_NLAG);
+    // CTR: [1] remove_doubling stream counter, [2] streams in CXL, [3] entries in XT, [4] streams in RXL,
+    //      [7] CXL entries already recomputed
     int* FLAG = reinterpret_cast<int*>(sm + OFF_FLAG);
     int* CXL = reinterpret_cast<int*>(sm + OFF_CXL);
     int* RXL = reinterpret_cast<int*>(sm + OFF_RXL);
-    float* CK = sm + OFF_CK;
-    int* CAND = reinterpret_cast<int*>(sm + OFF_CAND);
-    float* CEX = sm + OFF_CEX;
-    int* XT = reinterpret_cast<int*>(sm + OFF_XT);
-    float* MB = sm + OFF_MB;
-    int* NEEDX = reinterpret_cast<int*>(sm + OFF_NEEDX);
+    int* XT = reinterpret_cast<int*>(sm + OFF_XTL);
+    // per-stream views: selection scratch / fine-window results in SF, ladder scratch in the (dead) XC row
+    auto CANDp = [&](int s_) { return reinterpret_cast<int*>(SF + s_ * SF_LD + SO_CAND); };
+    auto CEXp = [&](int s_) { return SF + s_ * SF_LD + SO_CEX; };
+    auto FXp = [&](int s_) { return SF + s_ * SF_LD; };
+    auto IPRp = [&](int s_) { return XC + s_ * XC_LD + XO_IPR; };
+    auto LAGSp = [&](int s_) { return reinterpret_cast<int*>(XC + s_ * XC_LD + XO_LAGS); };
+    auto NLAGp = [&](int s_) { return reinterpret_cast<int*>(XC + s_ * XC_LD + XO_NLAG); };
+    auto YYSp = [&](int s_) { return XC + s_ * XC_LD + XO_YYS; };
+    auto YYKp = [&](int s_) { return XC + s_ * XC_LD + XO_YYK; };
+    // coarse running energy at lag i of stream s_ (src/pitch.rs:379-382, 401-402), replayed from the checkpoint at or below it
+    auto yn4_at = [&](int s_, int i) -> float {
+        const float* prow_ = P + s_ * P_LD;
+        float y = YNK[s_ * YNK_LD + (i >> 1)];
+        if (i & 1) {
+            const float a = prow_[2 * (N4 + i - 1)], b = prow_[2 * (i - 1)];
+            y = fmaxf(fa(y, fs(fm(a, a), fm(b, b))), 1.0f);
+        }
+        return y;
+    };
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ls = lane % SB;  // lane-per-stream phases: lanes >= SB mirror lanes < SB (same reads, same writes)
@@ -419,10 +434,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         } else {
             for (int i = lane; i < PB; i += 32) prow[i] = 0.0f;  // absent streams: zero rows
         }
-        if (lane < 4) {
-            prow[PB + lane] = 0.0f;
-            Y4[r * Y4_LD + PB / 2 + lane] = 0.0f;
-        }
+        if (lane < 4) prow[PB + lane] = 0.0f;
     }
     if (tid < 8) CTR[tid] = 0;
     if (tid < SB) FLAG[tid] = 0;
@@ -498,7 +510,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     __syncthreads();
     PPROF(2);
 
-    // ---- Ph4: fir5_in_place (src/pitch.rs:407-429) + second decimation (src/pitch.rs:74-79).
+    // ---- Ph4: fir5_in_place (src/pitch.rs:407-429).  (The second decimation, src/pitch.rs:74-79, is P read at stride 2.)
     // One warp per row, four samples per lane, 128-sample rounds from the END of the row backwards, so the five
     // older inputs a round needs are still un-filtered when it runs. ----
     for (int r = warp; r < SB; r += NW) {
@@ -522,27 +534,22 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
                               fm(nc[4], e[d]));
             }
             __syncwarp();
-            if (on) {
-                row4[q] = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float2*>(Y4 + r * Y4_LD + 2 * q) = make_float2(o[0], o[2]);
-            }
+            if (on) row4[q] = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
     __syncthreads();
     PPROF(3);
 
-    // ---- Warp roles from here on (NW = 8).  The two longest serial chains are taken off the critical path: they run on
-    // their own warps PAST the barriers of the phases that do not need their result (named barriers over subsets):
-    //   CKW (warp 5): fine running energy (needed in Ph8)           -- skips Ph5 .. Ph6b, rejoins before Ph8
-    //   YYW (warp 7): yy_lookup (needed by the ladder, Ph10)        -- leaves after Ph6x, rejoins before Ph9
-    //   G1 = all but CKW (7 warps, barrier 1): Ph5, Ph6a, Ph6x;  G2 = G1 without YYW (6 warps): Ph6b;
-    //   barrier 2 = G2 + CKW before Ph8;  barrier 0 = everybody.
+    // ---- Warp roles from here on (NW = 8).  Three serial chains run on their own warps beside the dense work:
+    //   CKW (warp 5): fine running energy (needed in Ph8), YNW (warp 6): coarse running energy -- both under the coarse
+    //                 cross-correlation of warps 0-4 (Ph5);
+    //   YYW (warp 7): energies in Ph5, then yy_lookup (needed from Ph9 on): it leaves after Ph6x and runs PAST the barrier
+    //                 of the fine search (named barrier 2 over the other seven warps), rejoining before Ph9.
     constexpr int CKW = NW - 3, YNW = NW - 2, YYW = NW - 1;
-    constexpr int G1N = (NW - 1) * 32;
+    constexpr int G1N = NT;
     static_assert(NW == 8, "warp roles assume 8 warps");
-    const int g1idx = warp < CKW ? warp : warp - 1;   // 0..6 over G1
-    const int g1tid = g1idx * 32 + lane;
-    float* YY = Y4;  // yy_lookup reuses the 4x-decimated copy once the coarse search is over
+    const int g1idx = warp;
+    const int g1tid = tid;
 
     if (warp == CKW) {
       if (lane < SB) {
@@ -570,69 +577,55 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             if ((m & 1) == 1) ck[(m + 1) >> 1] = y;  // after 4 (m + 1) steps
         }
       }
-    } else {
-        // ---- Ph5 (G1): two short serial jobs, then the coarse cross-correlation (FMA) ----
+    }
+    {
+        // ---- Ph5: two more serial jobs, and the coarse cross-correlation (FMA) ----
         if (warp == YNW && lane < SB) {
-            // y_sq_norm of find_best_pitch(xcorr, y_lp4, 240) (src/pitch.rs:379-382, 401-402); YN4[i] = value seen at lag i
-            const float4* row = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD);
+            // y_sq_norm of find_best_pitch(xcorr, y_lp4, 240) (src/pitch.rs:379-382, 401-402) over y_lp4[j] = p[2 j]; one
+            // checkpoint every second lag: YNK[m] = value seen at lag 2 m (yn4_at replays the odd lags' one step)
+            const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
             float y = 1.0f;
 #pragma unroll 4
-            for (int m = 0; m < N4 / 4; m++) {
+            for (int m = 0; m < N4 / 2; m++) {
                 const float4 v = row[m];
                 y = fa(y, fm(v.x, v.x));
-                y = fa(y, fm(v.y, v.y));
                 y = fa(y, fm(v.z, v.z));
-                y = fa(y, fm(v.w, v.w));
             }
-            float* out = YN4 + ls * XC_LD;
+            float* out = YNK + ls * YNK_LD;
             out[0] = y;
 #pragma unroll 2
-            for (int m = 0; m < NGRP; m++) {
-                const float4 va = row[N4 / 4 + m], vb = row[m];
-                const float a[4] = {va.x, va.y, va.z, va.w}, b[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-                for (int d = 0; d < 4; d++) {
-                    y = fmaxf(fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d]))), 1.0f);
-                    if (4 * m + d + 1 < XC_LD) out[4 * m + d + 1] = y;
-                }
+            for (int m = 0; m < NL4 / 2; m++) {  // two steps per float4, checkpoints up to lag 146
+                const float4 va = row[N4 / 2 + m], vb = row[m];
+                y = fmaxf(fa(y, fs(fm(va.x, va.x), fm(vb.x, vb.x))), 1.0f);
+                y = fmaxf(fa(y, fs(fm(va.z, va.z), fm(vb.z, vb.z))), 1.0f);
+                out[m + 1] = y;  // after 2 (m + 1) steps
             }
         } else if (warp == YYW) {
-            // Four energies, one code path for both half-warps (h = lane >> 4):
-            //   h = 0: xx = inner_prod(x, x, 480) with its four interleaved accumulators (src/pitch.rs:133, 225-244: EXACT,
-            //          it reaches last_gain), then sum x_lp4^2 = Y4[192..432)
-            //   h = 1: sum P[0..384)^2, then sum Y4[0..192)^2          (the last three only bound rounding errors)
+            // Four energies, one code path for both half-warps (h = lane >> 4), one pass over the row:
+            //   h = 0: p[384..864): xx = inner_prod(x, x, 480) with its four interleaved accumulators (src/pitch.rs:133,
+            //          225-244: EXACT, it reaches last_gain) and, from the even samples, sum x_lp4^2
+            //   h = 1: p[0..384): sum p^2 and, from the even samples, the rest of sum y_lp4^2   (these three only bound errors)
             const int h = lane >> 4;
             const float4* pr = reinterpret_cast<const float4*>(P + ls * P_LD) + (h ? 0 : HALF_MAX / 4);
             const int np = h ? HALF_MAX / 4 : HALF_N / 4;
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, e0 = 0.0f, e1 = 0.0f;
             unsigned nz = 0;  // does the row hold anything but (signed) zeros?  (a sum of squares may underflow to 0)
 #pragma unroll 4
             for (int m = 0; m < HALF_N / 4; m++) {
                 if (m < np) {
                     const float4 x = pr[m];
-                    a0 = fa(a0, fm(x.x, x.x));
+                    const float sx = fm(x.x, x.x), sz = fm(x.z, x.z);
+                    a0 = fa(a0, sx);
                     a1 = fa(a1, fm(x.y, x.y));
-                    a2 = fa(a2, fm(x.z, x.z));
+                    a2 = fa(a2, sz);
                     a3 = fa(a3, fm(x.w, x.w));
+                    e0 = fa(e0, sx);
+                    e1 = fa(e1, sz);
                     nz |= __float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) | __float_as_uint(x.w);
                 }
             }
             NZ[h * SB + ls] = (int)(nz & 0x7fffffffu);
-            const float sp = fa(fa(fa(a0, a1), a2), a3);
-            const float4* yr = reinterpret_cast<const float4*>(Y4 + ls * Y4_LD) + (h ? 0 : HALF_MAX / 8);
-            const int ny = h ? HALF_MAX / 8 : N4 / 4;
-            a0 = a1 = a2 = a3 = 0.0f;
-#pragma unroll 4
-            for (int m = 0; m < N4 / 4; m++) {
-                if (m < ny) {
-                    const float4 x = yr[m];
-                    a0 = fa(a0, fm(x.x, x.x));
-                    a1 = fa(a1, fm(x.y, x.y));
-                    a2 = fa(a2, fm(x.z, x.z));
-                    a3 = fa(a3, fm(x.w, x.w));
-                }
-            }
-            const float sy = fa(fa(fa(a0, a1), a2), a3);
+            const float sp = fa(fa(fa(a0, a1), a2), a3), sy = fa(e0, e1);
             if (h == 0) {
                 XX[ls] = sp;
                 BND[0 * SB + ls] = sy;
@@ -643,23 +636,24 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         }
         // coarse xcorr, FMA: lane-task = (stream, group of 16 consecutive lags): 160 tasks = warps 0-4 exactly
         if (warp < CKW) {
+            // stream-minor task order: the 8 lanes of a quarter-warp read the SAME columns of 8 DIFFERENT rows (row stride
+            // = 4 mod 32 words), so every LDS.128 is conflict-free; a lag-minor order put them 128 bytes apart in one row
             const int L = warp * 32 + lane;
-            const int s = L / 10, g = L - s * 10;
-            coarse_group16(Y4 + s * Y4_LD, g, XC + s * XC_LD);
+            const int s = L % SB, g = L / SB;
+            coarse_group16(P + s * P_LD, g, XC + s * XC_LD);
         }
         bar_sync(1, G1N);
         PPROF(4);
 
         // ---- Ph6a (G1): certified coarse selection, one warp per stream, lane = lags lane, lane + 32, ... (src/pitch.rs:83-84) ----
-        for (int s = g1idx; s < SB; s += NW - 1) {
+        for (int s = g1idx; s < SB; s += NW) {
             const float* xc = XC + s * XC_LD;
-            const float* yn = YN4 + s * XC_LD;
             float cv[NSLOT], yv[NSLOT];
 #pragma unroll
             for (int k = 0; k < NSLOT; k++) {
                 const int lag = lane + 32 * k;
                 cv[k] = lag < NL4 ? xc[lag] : 0.0f;
-                yv[k] = lag < NL4 ? yn[lag] : 1.0f;
+                yv[k] = lag < NL4 ? yn4_at(s, lag) : 1.0f;
             }
             // approximate top two by score c^2 / y (c > 0): ANY two distinct lags keep the certificate sound, so the scores
             // may be rounded freely (fast division) and the warp maxima taken on their bit patterns (scores >= 0)
@@ -705,7 +699,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             } else if (f1 < 0 || f2 < 0 || f2 == f1) {
                 cx = true;
             } else {
-                const float c1 = xc[f1], c2 = xc[f2], y1 = yn[f1], y2 = yn[f2];
+                const float c1 = xc[f1], c2 = xc[f2], y1 = yn4_at(s, f1), y2 = yn4_at(s, f2);
                 const float a1 = c1 - delta, a2 = c2 - delta;
                 if (!(a1 > 0.0f) || !(a2 > 0.0f) || !(a1 * a1 > 1e-20f) || !(a2 * a2 > 1e-20f)) {
                     cx = true;
@@ -736,7 +730,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
                         int basek = 0;  // candidates in ascending lag order: slot-major, lane-minor
 #pragma unroll
                         for (int k = 0; k < NSLOT; k++) {
-                            if ((inmask >> k) & 1u) CAND[s * CMAX + basek + __popc(masks[k] & ((1u << lane) - 1u))] = lane + 32 * k;
+                            if ((inmask >> k) & 1u) CANDp(s)[basek + __popc(masks[k] & ((1u << lane) - 1u))] = lane + 32 * k;
                             basek += __popc(masks[k]);
                         }
                         if (nc == 2 && lo1 > hi2 * ETA1) {         // lo_F1 > hi_F2 (1 + eta)
@@ -748,7 +742,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
                         } else {
                             need = true;
                         }
-                        if (lane == 0) MB[s] = mbound;
+                        if (lane == 0) SF[s * SF_LD + SO_MB] = mbound;
                     }
                 }
             }
@@ -756,7 +750,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             if (lane == 0) {
                 SI[0 * SB + s] = best;
                 SI[1 * SB + s] = second;
-                NEEDX[s] = need ? nc : 0;
+                reinterpret_cast<int*>(SF)[s * SF_LD + SO_NEEDX] = need ? nc : 0;
                 if (cx) {
                     FLAG[s] = 1;
                     CXL[atomicAdd(&CTR[2], 1)] = s;
@@ -776,49 +770,52 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             if (ncx == ncx_lo && nx == 0) break;  // uniform over G1
             for (int L = g1tid; L < nx; L += G1N) {
                 const int e = XT[L], s = e >> 8, pos = e & 255;
-                const int lag = CAND[s * CMAX + pos];
-                const float4* xr = reinterpret_cast<const float4*>(Y4 + s * Y4_LD + HALF_MAX / 2);
-                const float* yr = Y4 + s * Y4_LD + lag;
-                float c = 0.0f;  // src/pitch.rs:296-363: one accumulator per lag, j ascending
+                const int lag = CANDp(s)[pos];
+                const float* prow = P + s * P_LD;
+                const float4* xr = reinterpret_cast<const float4*>(prow + HALF_MAX);
+                const float* yr = prow + 2 * lag;
+                float c = 0.0f;  // src/pitch.rs:296-363: one accumulator per lag, j ascending; x_lp4[j] = p[384 + 2 j], y_lp4[j] = p[2 j]
 #pragma unroll 4
                 for (int m = 0; m < N4 / 4; m++) {
-                    const float4 x = xr[m];
-                    c = fa(c, fm(x.x, yr[4 * m]));
-                    c = fa(c, fm(x.y, yr[4 * m + 1]));
-                    c = fa(c, fm(x.z, yr[4 * m + 2]));
-                    c = fa(c, fm(x.w, yr[4 * m + 3]));
+                    const float4 xa = xr[2 * m], xb = xr[2 * m + 1];
+                    c = fa(c, fm(xa.x, yr[8 * m]));
+                    c = fa(c, fm(xa.z, yr[8 * m + 2]));
+                    c = fa(c, fm(xb.x, yr[8 * m + 4]));
+                    c = fa(c, fm(xb.z, yr[8 * m + 6]));
                 }
-                CEX[s * CMAX + pos] = c;
+                CEXp(s)[pos] = c;
             }
-            for (int L = g1tid; L < (ncx - ncx_lo) * 40; L += G1N) {
-                const int i = L / 40, g = L - i * 40;
-                if (g < NGRP) {
-                    const int s = CXL[ncx_lo + i];
-                    coarse_group<true>(Y4 + s * Y4_LD, g, XC + s * XC_LD);
-                }
+            for (int L = g1tid; L < (ncx - ncx_lo) * NGRP; L += G1N) {  // stream-minor, like the FMA pass
+                const int nst = ncx - ncx_lo, i = L % nst, g = L / nst;
+                const int s = CXL[ncx_lo + i];
+                coarse_group4_exact(P + s * P_LD, g, XC + s * XC_LD);
             }
             bar_sync(1, G1N);
             if (warp == 0 && lane < SB) {
                 const int s = lane;
                 const float* xc = XC + s * XC_LD;
-                const float* yn = YN4 + s * XC_LD;
                 const int fl = FLAG[s];
+                const int needx = reinterpret_cast<const int*>(SF)[s * SF_LD + SO_NEEDX];
                 if ((fl & 1) && !(fl & 4)) {
-                    // the reference's scan over all lags on exact values
+                    // the reference's scan over all lags on exact values; its running energy advances with it
                     BestTwo b2;
-#pragma unroll 7
-                    for (int i = 0; i < NL4; i++) b2.consider(i, xc[i], yn[i]);
+                    const float* prow = P + s * P_LD;
+                    float y = YNK[s * YNK_LD];
+                    for (int i = 0; i < NL4; i++) {
+                        b2.consider(i, xc[i], y);
+                        const float a = prow[2 * (N4 + i)], b = prow[2 * i];
+                        y = fmaxf(fa(y, fs(fm(a, a), fm(b, b))), 1.0f);
+                    }
                     SI[0 * SB + s] = b2.best;
                     SI[1 * SB + s] = b2.second;
                     FLAG[s] = fl | 4;
-                } else if (round == 0 && NEEDX[s] > 0) {
-                    const int nc = NEEDX[s];
-                    const float mbound = MB[s];
+                } else if (round == 0 && needx > 0) {
+                    const float mbound = SF[s * SF_LD + SO_MB];
                     BestTwo b2;
                     bool ok = true;
-                    for (int k = 0; k < nc; k++) {
-                        const int lag = CAND[s * CMAX + k];
-                        const float c = CEX[s * CMAX + k], ysq = yn[lag];
+                    for (int k = 0; k < needx; k++) {
+                        const int lag = CANDp(s)[k];
+                        const float c = CEXp(s)[k], ysq = yn4_at(s, lag);
                         // every candidate must beat the upper bound of every non-candidate robustly
                         if (!(c > 0.0f) || !(__fdividef(c * c, ysq) > mbound * ETA1)) ok = false;
                         b2.consider(lag, c, ysq);
@@ -840,10 +837,11 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
 
         if (warp == YYW) {
           if (lane < SB) {
-            // yy_lookup (src/pitch.rs:135-142): stored clamped at 0, carried unclamped; i = 1..384 walks the rows downwards.
-            // Runs beside the fine search (the 4x-decimated copy it overwrites is dead after Ph6x).
+            // yy_lookup (src/pitch.rs:135-142): carried unclamped, i = 1..384 walks the rows downwards; one checkpoint every
+            // 16 lags (YYK[m] = unclamped value at lag 16 m), the lags the ladder reads are replayed from them in Ph9.
+            // Runs beside the fine search (the XC row it writes into is dead after Ph6x).
             const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
-            float* out = YY + ls * YY_LD;
+            float* out = YYKp(ls);
             float y = XX[ls];
             out[0] = y;
 #pragma unroll 2
@@ -852,14 +850,12 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
                 const float4 vb = row[(HALF_MAX + HALF_N) / 4 - 1 - m];   // p[860-4m .. 863-4m]
                 const float a[4] = {va.w, va.z, va.y, va.x}, b[4] = {vb.w, vb.z, vb.y, vb.x};
 #pragma unroll
-                for (int d = 0; d < 4; d++) {
-                    y = fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d])));
-                    out[4 * m + d + 1] = fmaxf(y, 0.0f);
-                }
+                for (int d = 0; d < 4; d++) y = fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d])));
+                if ((m & 3) == 3) out[(m + 1) >> 2] = y;  // after 4 (m + 1) steps
             }
           }
         } else {
-            // ---- Ph6b (G2): the two 5-lag fine windows of every stream (src/pitch.rs:88-96).  Each window i0c .. i0c+4 (i0c =
+            // ---- Ph6b (all but YYW): the two 5-lag fine windows of every stream (src/pitch.rs:88-96).  Each window i0c .. i0c+4 (i0c =
             // start clamped into the valid range) lies inside the ALIGNED 8 lags a .. a+7, a = i0c & ~3, computed as two 4-lag
             // sliding windows on 128-bit reads: 64 lane-tasks (stream, window, half) = warps 0 and 1.  Which lags count as
             // candidates is decided in Ph8. ----
@@ -873,17 +869,17 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
                 inner_prod_window4_aligned(reinterpret_cast<const float4*>(prow + HALF_MAX),
                                            reinterpret_cast<const float4*>(prow + a + 4 * half), out);
 #pragma unroll
-                for (int c = 0; c < 4; c++) FX[s * FX_LD + wdw * 8 + half * 4 + c] = fmaxf(out[c], -1.0f);
+                for (int c = 0; c < 4; c++) FXp(s)[wdw * 8 + half * 4 + c] = fmaxf(out[c], -1.0f);
             }
         }
     }
-    if (warp != YYW) bar_sync(2, G1N);  // G2 + CKW: FX and CK complete
+    if (warp != YYW) bar_sync(2, NT - 32);  // everybody but YYW: FX complete
     PPROF(7);
 
     // ---- Ph8: fine best + pseudo-interpolation (src/pitch.rs:97-114), lane = stream ----
     if (warp == 0 && lane < SB) {
         const int best4 = SI[0 * SB + ls], second4 = SI[1 * SB + ls];
-        const float* fx = FX + ls * FX_LD;
+        const float* fx = FXp(ls);
         // fine running energy at lag i, replayed from the nearest checkpoint at or below it (lags are asked in
         // ascending order): step i -> i + 1 is y = max(y + p[480 + i]^2 - p[i]^2, 1)  (src/pitch.rs:401-402)
         const float* prow8 = P + ls * P_LD;
@@ -933,7 +929,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         // (k is a compile-time constant in the unrolled loops below: the divisions by 2k become multiply-shifts)
         {
             SI[2 * SB + ls] = t0;
-            int* lg = LAGS + ls * LAG_LD;
+            int* lg = LAGSp(ls);
             lg[0] = t0;
             int nk = 0;
 #pragma unroll
@@ -947,7 +943,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
                     nk++;
                 }
             }
-            NLAG[ls] = 1 + 2 * nk;
+            *NLAGp(ls) = 1 + 2 * nk;
         }
     }
     __syncthreads();  // everybody: LAGS written, yy_lookup complete
@@ -965,8 +961,20 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         float xr[15];
 #pragma unroll
         for (int j = 0; j < 15; j++) xr[j] = pl[j];
-        const int n = NLAG[s];
-        const int* lg = LAGS + s * LAG_LD;
+        const int n = *NLAGp(s);
+        const int* lg = LAGSp(s);
+        // yy_lookup at this stream's lags: lane i replays lag lg[i] from the checkpoint at or below it (same operations in the
+        // same order as the chain: the same bits); stored clamped at 0 like the reference's table
+        if (lane < n) {
+            const int L = lg[lane];
+            const float* prow = P + s * P_LD;
+            float y = YYKp(s)[L / YYK_STEP];
+            for (int i = (L / YYK_STEP) * YYK_STEP + 1; i <= L; i++) {
+                const float a = prow[HALF_MAX - i], b = prow[HALF_MAX + HALF_N - i];
+                y = fa(y, fs(fm(a, a), fm(b, b)));
+            }
+            YYSp(s)[lane] = fmaxf(y, 0.0f);
+        }
         for (int base = 0; base < n; base += 8) {
             float acc[8];
 #pragma unroll
@@ -998,7 +1006,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
             acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
             const int idx = base + (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
-            if ((lane & 3) == 0 && idx < n) IPR[s * IPR_LD + 1 + idx] = acc[0];
+            if ((lane & 3) == 0 && idx < n) IPRp(s)[1 + idx] = acc[0];
         }
     }
     __syncthreads();
@@ -1006,15 +1014,16 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
 
     // ---- Ph10a: the sub-harmonic ladder (src/pitch.rs:144-203) on the fast inner products, every decision certified ----
     // exact == false: fast values with margins; exact == true (only for streams in RXL): the same code on exact values.
-    auto ladder = [&](bool exact, int& t_out, int& t1b_out, bool& uncertain) {
-        const float* ipr = IPR + ls * IPR_LD;
-        const float* yy = YY + ls * YY_LD;
+    // yy_lookup values come from YYS: position 0 = lag t0, positions 1 + 2 (k - 2) and 2 + 2 (k - 2) = lags t1, t1b of step k
+    auto ladder = [&](bool exact, int& t_out, int& t1b_out, int& pos_out, bool& uncertain) {
+        const float* ipr = IPRp(ls);
+        const float* yys = YYSp(ls);
         const int t0 = SI[2 * SB + ls];
         const float xx = XX[ls];
         const float dip = exact ? 0.0f : KAPPA2 * sqrtf(xx * (BND[1 * SB + ls] + xx)) * 1.001f;
         uncertain = !(dip < 1e30f);
         const float xy0 = ipr[1];
-        const float yy0 = yy[t0];
+        const float yy0 = yys[0];
         int prev_period = 0;
         float lg = 0.0f;
         if (ls < ns) {
@@ -1023,7 +1032,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
         }
         const float g0 = pitch_gain(xy0, xx, yy0);
         const float dg0 = __fdiv_rn(dip, __fsqrt_rn(fa(1.0f, fm(xx, yy0))));
-        int t = t0, t1bs = t0;
+        int t = t0, t1bs = t0, pos = 0;
 #pragma unroll
         for (int k = 2; k <= 12; k++) {
             constexpr int sc[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};  // SECOND_CHECK, src/pitch.rs:489
@@ -1033,7 +1042,7 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             if (k == 2) t1b = (t1 + t0 > HALF_MAX) ? t0 : t0 + t1;
             else t1b = (2 * sc[k] * t0 + k) / (2 * k);
             const float xy = fm(fa(ipr[2 + 2 * (k - 2)], ipr[3 + 2 * (k - 2)]), 0.5f);
-            const float yyv = fm(fa(yy[t1], yy[t1b]), 0.5f);
+            const float yyv = fm(fa(yys[1 + 2 * (k - 2)], yys[2 + 2 * (k - 2)]), 0.5f);
             const float g1 = pitch_gain(xy, xx, yyv);
             const int d = abs(t1 - prev_period);
             float cont;
@@ -1051,19 +1060,22 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             if (g1 > thresh) {
                 t = t1;
                 t1bs = t1b;
+                pos = 1 + 2 * (k - 2);
             }
         }
         t_out = t;
         t1b_out = t1bs;
+        pos_out = pos;
     };
     if (warp == 0 && lane < SB) {
-        int t, t1b;
+        int t, t1b, pos;
         bool unc;
-        ladder(false, t, t1b, unc);
+        ladder(false, t, t1b, pos, unc);
         if (force_exact & 2) unc = true;
         {
             SI[3 * SB + ls] = t;
             SI[4 * SB + ls] = t1b;
+            SI[5 * SB + ls] = pos;
             if (unc) {
                 FLAG[ls] |= 2;
                 RXL[atomicAdd(&CTR[4], 1)] = ls;
@@ -1080,20 +1092,20 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
             for (int L = tid; L < nrx * LAG_LD; L += NT) {
                 const int i = L / LAG_LD, q = L - i * LAG_LD;
                 const int s = RXL[i];
-                if (q < NLAG[s]) {
+                if (q < *NLAGp(s)) {
                     const float* prow = P + s * P_LD;
-                    IPR[s * IPR_LD + 1 + q] =
-                        inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - LAGS[s * LAG_LD + q]);
+                    IPRp(s)[1 + q] = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - LAGSp(s)[q]);
                 }
             }
             __syncthreads();
             if (warp == 0 && lane < SB && (FLAG[ls] & 2)) {
-                int t, t1b;
+                int t, t1b, pos;
                 bool dummy;
-                ladder(true, t, t1b, dummy);
+                ladder(true, t, t1b, pos, dummy);
                 {
                     SI[3 * SB + ls] = t;
                     SI[4 * SB + ls] = t1b;
+                    SI[5 * SB + ls] = pos;
                 }
             }
             __syncthreads();
@@ -1103,26 +1115,28 @@ __global__ void __launch_bounds__(NT, 2) pitch_kernel(const float* __restrict__ 
     // ---- Ph11: what reaches the state and the output is always order-exact: the +-1 refinement (src/pitch.rs:205-218)
     // and last_gain (:199-203).  Four single-lag lane-tasks per stream -- lags t+1, t, t-1 and t1b (the second inner
     // product behind best_xy) -- on two warps, then one lane per stream finishes. ----
-    float* XF = FX;  // [SB][4] in the (dead) fine-window buffer
+    // (the four results go to the first entries of the dead fine-window row)
     if (warp < 2) {
         const int s = 8 * warp + (lane >> 2), j = lane & 3;
         const int t = SI[3 * SB + s], t1b = SI[4 * SB + s];
         const float* prow = P + s * P_LD;
-        XF[s * FX_LD + j] = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (j < 3 ? t + 1 - j : t1b));
+        FXp(s)[j] = inner_prod_480(reinterpret_cast<const float4*>(prow + HALF_MAX), prow + HALF_MAX - (j < 3 ? t + 1 - j : t1b));
     }
     __syncthreads();
     if (warp == 0 && lane < SB) {
         const int t = SI[3 * SB + ls], t1b = SI[4 * SB + ls], t0 = SI[2 * SB + ls];
-        const float* yy = YY + ls * YY_LD;
+        const float* yys = YYSp(ls);
+        const int pos = SI[5 * SB + ls];
         const float xx = XX[ls];
-        const float x_2 = XF[ls * FX_LD + 0], x_1 = XF[ls * FX_LD + 1], x_0 = XF[ls * FX_LD + 2], ipb = XF[ls * FX_LD + 3];  // x_k: lag t - 1 + k
+        const float* xf = FXp(ls);
+        const float x_2 = xf[0], x_1 = xf[1], x_0 = xf[2], ipb = xf[3];  // x_k: lag t - 1 + k
         float best_xy, best_yy;
         if (t == t0) {  // no sub-harmonic accepted (an accepted t1 is always < t0)
             best_xy = x_1;
-            best_yy = yy[t0];
+            best_yy = yys[0];
         } else {
             best_xy = fm(fa(x_1, ipb), 0.5f);
-            best_yy = fm(fa(yy[t], yy[t1b]), 0.5f);
+            best_yy = fm(fa(yys[pos], yys[pos + 1]), 0.5f);
         }
         const float g = pitch_gain(best_xy, xx, best_yy);
         best_xy = fmaxf(best_xy, 0.0f);

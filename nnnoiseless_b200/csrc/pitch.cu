@@ -75,7 +75,7 @@ constexpr int MIN_PERIOD2 = PITCH_MIN_PERIOD / 2;                      // 30
 constexpr int P_LD = 868;
 constexpr int XC_LD = 149;
 constexpr int YNK_LD = 75;   // checkpoints of the coarse running energy (every second lag: 74 values)
-constexpr int YYK_STEP = 16;
+constexpr int YYK_STEP = 8;
 constexpr int IPR_LD = 31;
 constexpr int FX_LD = 17;  // two aligned 8-lag fine windows per stream
 constexpr int NGRP = (NL4 + 3) / 4;  // 37 lag groups of 4
@@ -114,7 +114,7 @@ constexpr int XO_IPR = 0;                          // [31]
 constexpr int XO_LAGS = 32;                        // int [24]
 constexpr int XO_NLAG = 56;                        // int
 constexpr int XO_YYS = 57;                         // [24]  yy_lookup at the lags of LAGS
-constexpr int XO_YYK = 81;                         // [25]  yy_lookup checkpoints (lag 16 m)
+constexpr int XO_YYK = 81;                         // [49]  yy_lookup checkpoints (lag 8 m)
 static_assert(XO_YYK + HALF_MAX / YYK_STEP + 1 <= XC_LD, "ladder scratch must fit in the XC row");
 // inside a stream's SF row
 constexpr int SO_CAND = 0, SO_CEX = CMAX, SO_MB = 2 * CMAX, SO_NEEDX = 2 * CMAX + 1;
@@ -260,9 +260,36 @@ __device__ __forceinline__ void inner_prod_window4_aligned(const float4* __restr
     for (int c = 0; c < 4; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
 }
 
+// Two consecutive lags of inner_prod(x, y + lag, 480) starting at an 8-byte aligned y (64-bit reads):
+// acc[c][u] is the reference's accumulator u of lag c.
+__device__ __forceinline__ void inner_prod_window2_aligned(const float4* __restrict__ xr, const float2* __restrict__ yr, float* out) {
+    float acc[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[c][u] = 0.0f;
+    float2 w0 = yr[0], w1 = yr[1];
+#pragma unroll 4
+    for (int m = 0; m < HALF_N / 4; m++) {
+        const float4 x = xr[m];
+        const float2 w2 = yr[2 * m + 2];
+        const float e[5] = {w0.x, w0.y, w1.x, w1.y, w2.x};
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) acc[c][u] = fa(acc[c][u], fm(xv[u], e[u + c]));
+        w0 = w2;
+        w1 = yr[2 * m + 3];
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
+}
+
 // Sixteen consecutive coarse lags 16g..16g+15 of one stream, FMA (certified afterwards).  The 4x-decimated operands are the
-// even samples of the whitened row: x_lp4[j] = p[384 + 2 j], y_lp4[j] = p[2 j] (src/pitch.rs:74-79), two per LDS.128.
-// Four LDS.128 per 64 multiply-adds.
+// even samples of the whitened row: x_lp4[j] = p[384 + 2 j], y_lp4[j] = p[2 j] (src/pitch.rs:74-79).  (ptxas splits the
+// 128-bit reads into the two 32-bit halves that are used; forcing LDS.128 with ld.volatile removes 210 of the 1850
+// shared-memory wavefronts per stream and was measured no faster -- the kernel is not wavefront-bound.)
 __device__ __forceinline__ void coarse_group16(const float* __restrict__ prow, int g, float* __restrict__ xcrow) {
     const float4* xr = reinterpret_cast<const float4*>(prow + HALF_MAX);
     const float4* yr = reinterpret_cast<const float4*>(prow + 32 * g);
@@ -838,7 +865,7 @@ __global__ void __launch_bounds__(NT, 3) pitch_kernel(const float* __restrict__ 
         if (warp == YYW) {
           if (lane < SB) {
             // yy_lookup (src/pitch.rs:135-142): carried unclamped, i = 1..384 walks the rows downwards; one checkpoint every
-            // 16 lags (YYK[m] = unclamped value at lag 16 m), the lags the ladder reads are replayed from them in Ph9.
+            // 8 lags (YYK[m] = unclamped value at lag 8 m), the lags the ladder reads are replayed from them in Ph9.
             // Runs beside the fine search (the XC row it writes into is dead after Ph6x).
             const float4* row = reinterpret_cast<const float4*>(P + ls * P_LD);
             float* out = YYKp(ls);
@@ -851,25 +878,25 @@ __global__ void __launch_bounds__(NT, 3) pitch_kernel(const float* __restrict__ 
                 const float a[4] = {va.w, va.z, va.y, va.x}, b[4] = {vb.w, vb.z, vb.y, vb.x};
 #pragma unroll
                 for (int d = 0; d < 4; d++) y = fa(y, fs(fm(a[d], a[d]), fm(b[d], b[d])));
-                if ((m & 3) == 3) out[(m + 1) >> 2] = y;  // after 4 (m + 1) steps
+                if ((m & 1) == 1) out[(m + 1) >> 1] = y;  // after 4 (m + 1) steps
             }
           }
         } else {
             // ---- Ph6b (all but YYW): the two 5-lag fine windows of every stream (src/pitch.rs:88-96).  Each window i0c .. i0c+4 (i0c =
-            // start clamped into the valid range) lies inside the ALIGNED 8 lags a .. a+7, a = i0c & ~3, computed as two 4-lag
-            // sliding windows on 128-bit reads: 64 lane-tasks (stream, window, half) = warps 0 and 1.  Which lags count as
-            // candidates is decided in Ph8. ----
-            if (warp < 2) {
+            // start clamped into the valid range) lies inside the EVEN-aligned 6 lags a .. a+5, a = i0c & ~1, computed as three 2-lag
+            // sliding windows: 96 lane-tasks (stream, window, pair of lags) = warps 0-2, 64-bit reads of the lagged row.
+            // Which lags count as candidates is decided in Ph8. ----
+            if (warp < 3) {
                 const int L = warp * 32 + lane;
-                const int s = L >> 2, wdw = (L >> 1) & 1, half = L & 1;
+                const int s = L / 6, r6 = L - 6 * s, wdw = r6 / 3, qt = r6 - 3 * wdw;
                 const int ctr = 2 * SI[wdw * SB + s];
-                const int a = min(max(ctr - 2, 0), NL2 - 5) & ~3;
+                const int a = min(max(ctr - 2, 0), NL2 - 5) & ~1;
                 const float* prow = P + s * P_LD;
-                float out[4];
-                inner_prod_window4_aligned(reinterpret_cast<const float4*>(prow + HALF_MAX),
-                                           reinterpret_cast<const float4*>(prow + a + 4 * half), out);
-#pragma unroll
-                for (int c = 0; c < 4; c++) FXp(s)[wdw * 8 + half * 4 + c] = fmaxf(out[c], -1.0f);
+                float out[2];
+                inner_prod_window2_aligned(reinterpret_cast<const float4*>(prow + HALF_MAX),
+                                           reinterpret_cast<const float2*>(prow + a + 2 * qt), out);
+                FXp(s)[wdw * 8 + 2 * qt] = fmaxf(out[0], -1.0f);
+                FXp(s)[wdw * 8 + 2 * qt + 1] = fmaxf(out[1], -1.0f);
             }
         }
     }
@@ -904,8 +931,8 @@ __global__ void __launch_bounds__(NT, 3) pitch_kernel(const float* __restrict__ 
         // xcorr at fine lag i: computed iff |i - 2 best| <= 2 or |i - 2 second| <= 2 (src/pitch.rs:90-95), else 0
         auto xcf = [&](int i) -> float {
             if (i < 0 || i >= NL2) return 0.0f;
-            if (abs(i - cA) <= 2) return fx[i - (baseA & ~3)];
-            if (abs(i - cB) <= 2) return fx[8 + i - (baseB & ~3)];
+            if (abs(i - cA) <= 2) return fx[i - (baseA & ~1)];
+            if (abs(i - cB) <= 2) return fx[8 + i - (baseB & ~1)];
             return 0.0f;
         };
         BestTwo b2;

@@ -18,12 +18,13 @@ __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); 
 // ================================================================================================
 // K1: high-pass biquad, one lane per stream (src/util.rs:95-107: f64 arithmetic, f32 state, 480 dependent
 // steps per frame).  The recurrence cannot be re-associated, so throughput comes from running many of them
-// side by side: 128 streams per block (one per thread), four blocks per SM.  The [128][480] input is streamed
+// side by side: 64 streams per block (one per thread; 1024 blocks at 65,536 streams = 6.9 per SM -- with 128 the single
+// wave left SMs with 3 or 4 blocks, a 15 % imbalance).  The [64][480] input is streamed
 // in six 80-sample chunks staged through shared memory, so global traffic is coalesced 128-bit while each
 // lane walks its own row (stride 81 words: conflict-free).
 // ================================================================================================
-constexpr int HP_STREAMS = 128;
-constexpr int HP_THREADS = 128;
+constexpr int HP_STREAMS = 64;
+constexpr int HP_THREADS = 64;
 constexpr int HP_CHUNK = 80;
 constexpr int HP_LD = HP_CHUNK + 1;
 static_assert(FRAME_SIZE % HP_CHUNK == 0 && HP_CHUNK % 4 == 0, "chunking must tile the frame");

@@ -53,8 +53,8 @@ KERNEL_BYTES = {
     "rnn": 168 + 672 + 4 + 672 + 88 + 4,
     "synthesis": 3848 + 3200 + 3 * 88 + 88 + 88 + 88 + 1920 + 1920 + 1920 + 4,
 }
-KERNEL_PATTERNS = {"hp_filter": "hp_filter_kernel", "pitch": "pitch_kernel", "analysis": "analysis_kernel",
-                   "rnn": "rnn_", "synthesis": "synthesis_kernel"}
+KERNEL_PATTERNS = {"hp_filter": "hp_filter_kernel", "pitch": "pitch_kernel", "analysis": "analysis_",
+                   "rnn": "rnn_", "synthesis": "synthesis_"}
 
 
 def load_peaks():

@@ -465,19 +465,6 @@ __global__ void __launch_bounds__(NT, 3) pitch_kernel(const float* __restrict__ 
     }
     if (tid < 8) CTR[tid] = 0;
     if (tid < SB) FLAG[tid] = 0;
-    {
-        // The block that takes this one's place is about one resident wave ahead (blocks are dispatched in index order,
-        // three per SM): ask L2 for its history rows now, so that its Ph1 finds them there instead of in HBM.
-        constexpr int LINES = (PITCH_BUF_SIZE * 4 + 127) / 128;  // 54 lines of 128 B per stream
-        const int sn0 = s0 + 148 * 3 * SB;
-        const int nn = min(SB, n_streams - sn0);
-        for (int i = tid; i < nn * LINES; i += NT) {
-            const int r = i / LINES, l = i - r * LINES;
-            int o = hbase * 4 + 128 * l;
-            if (o >= HIST_CAP * 4) o -= HIST_CAP * 4;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(hist + (size_t)(sn0 + r) * HIST_CAP) + o));
-        }
-    }
     __syncthreads();
     PPROF(0);
 

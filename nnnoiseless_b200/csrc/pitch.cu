@@ -29,7 +29,7 @@
 // (stream, lag-group) lane-tasks with register sliding windows, or one warp per stream with the 480 samples
 // dealt to the lanes (15 each: conflict-free scalar reads for arbitrary lags, x held in registers).
 //
-// Shared-memory tile (dynamic, SB = 16 streams per block -> 73 KB, THREE blocks per SM: the serial phases of one block
+// Shared-memory tile (dynamic, SB = 16 streams per block -> 75.7 KB, THREE blocks per SM: the serial phases of one block
 // hide behind the dense phases of two others):
 //   P   [SB][868]  2x-decimated, LPC-whitened history (pitch_buf); row stride 868 = 16B aligned and
 //                  = 4 (mod 32) so that lane-per-stream float4 reads are bank-conflict free.  The 4x-decimated
@@ -37,7 +37,7 @@
 //   XC  [SB][149]  coarse cross-correlation; dead after the coarse search, then: IPR | LAGS | NLAG | YYS | YYK
 //   YNK [SB][75]   coarse running energy (exact), every second lag (the odd lags are one replayed step away)
 //   CK  [SB][39]   fine running energy, one checkpoint every 8 lags
-//   YYK [SB][25]   yy_lookup, one checkpoint every 16 lags; YYS [SB][24] its values at the lags the ladder reads
+//   YYK [SB][49]   yy_lookup, one checkpoint every 8 lags; YYS [SB][24] its values at the lags the ladder reads
 // All three running energies are sequential recurrences; a replay from a checkpoint repeats the same operations in the
 // same order, hence the same bits.
 #include <atomic>
@@ -59,7 +59,7 @@ __device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf
 #ifndef PITCH_NT
 #define PITCH_NT 256
 #endif
-constexpr int SB = PITCH_SB;    // streams per block (lane-per-stream phases use lanes 0..SB-1, mirrored on the others)
+constexpr int SB = PITCH_SB;    // streams per block (lane-per-stream phases use lanes 0..SB-1, the others predicated off)
 constexpr int NT = PITCH_NT;    // threads per block
 constexpr int NW = NT / 32;
 static_assert(SB == 16 && NW >= 4, "phase-to-warp assignment below assumes 16 streams and >= 4 warps");
@@ -76,8 +76,7 @@ constexpr int P_LD = 868;
 constexpr int XC_LD = 149;
 constexpr int YNK_LD = 75;   // checkpoints of the coarse running energy (every second lag: 74 values)
 constexpr int YYK_STEP = 8;
-constexpr int IPR_LD = 31;
-constexpr int FX_LD = 17;  // two aligned 8-lag fine windows per stream
+constexpr int FX_LD = 17;  // two fine windows per stream (6 even-aligned lags each, at offsets 0 and 8)
 constexpr int NGRP = (NL4 + 3) / 4;  // 37 lag groups of 4
 constexpr int CMAX = 8;              // coarse candidates recomputed exactly per stream
 constexpr int LAG_LD = 24;           // remove_doubling lags per stream: 1 + 2 * 11 (k <= 12 because t1 >= 30, t0 <= 383)
@@ -204,60 +203,6 @@ __device__ __forceinline__ float inner_prod_480(const float4* __restrict__ xr, c
         s3 = fa(s3, fm(x.w, y[4 * m + 3]));
     }
     return fa(fa(fa(s0, s1), s2), s3);
-}
-
-// NLAG consecutive lags of inner_prod(x, y + lag, 480) for one stream with ONE sliding register window over y:
-// acc[c][u] is the reference's accumulator u of lag c (src/pitch.rs:225-244), y read once.
-template <int NLAG>
-__device__ __forceinline__ void inner_prod_window(const float4* __restrict__ xr, const float* __restrict__ y, float* out) {
-    float acc[NLAG][4];
-#pragma unroll
-    for (int c = 0; c < NLAG; c++)
-#pragma unroll
-        for (int u = 0; u < 4; u++) acc[c][u] = 0.0f;
-    float w[8];
-#pragma unroll
-    for (int u = 0; u < 4; u++) w[u] = y[u];
-#pragma unroll 2
-    for (int m = 0; m < HALF_N / 4; m++) {
-        const float4 x = xr[m];
-        const float xv[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int u = 0; u < 4; u++) w[4 + u] = y[4 * m + 4 + u];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int c = 0; c < NLAG; c++) acc[c][u] = fa(acc[c][u], fm(xv[u], w[u + c]));
-#pragma unroll
-        for (int u = 0; u < 4; u++) w[u] = w[4 + u];
-    }
-#pragma unroll
-    for (int c = 0; c < NLAG; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
-}
-
-// Four consecutive lags of inner_prod(x, y + lag, 480) starting at a 16-byte aligned y (128-bit reads only: lanes of
-// different streams hit different rows, conflict-free): acc[c][u] is the reference's accumulator u of lag c.
-__device__ __forceinline__ void inner_prod_window4_aligned(const float4* __restrict__ xr, const float4* __restrict__ yr, float* out) {
-    float acc[4][4];
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-#pragma unroll
-        for (int u = 0; u < 4; u++) acc[c][u] = 0.0f;
-    float4 w = yr[0];
-#pragma unroll 2
-    for (int m = 0; m < HALF_N / 4; m++) {
-        const float4 x = xr[m];
-        const float4 wn = yr[m + 1];
-        const float e[8] = {w.x, w.y, w.z, w.w, wn.x, wn.y, wn.z, wn.w};
-        const float xv[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) acc[c][u] = fa(acc[c][u], fm(xv[u], e[u + c]));
-        w = wn;
-    }
-#pragma unroll
-    for (int c = 0; c < 4; c++) out[c] = fa(fa(fa(acc[c][0], acc[c][1]), acc[c][2]), acc[c][3]);
 }
 
 // Two consecutive lags of inner_prod(x, y + lag, 480) starting at an 8-byte aligned y (64-bit reads):
@@ -1151,7 +1096,7 @@ __global__ void __launch_bounds__(NT, 3) pitch_kernel(const float* __restrict__ 
     }
     __syncthreads();
     if (warp == 0 && lane < SB) {
-        const int t = SI[3 * SB + ls], t1b = SI[4 * SB + ls], t0 = SI[2 * SB + ls];
+        const int t = SI[3 * SB + ls], t0 = SI[2 * SB + ls];
         const float* yys = YYSp(ls);
         const int pos = SI[5 * SB + ls];
         const float xx = XX[ls];

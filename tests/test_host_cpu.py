@@ -151,3 +151,19 @@ def test_tcgen05_weight_packing_selftest(builtin_bytes, sh_bytes):
         for seed in range(8):
             assert 0.0 <= L.nnb_tc_pack_selftest(model, len(model), seed) < 2e-5
     assert L.nnb_tc_pack_selftest(builtin_bytes[:-1], len(builtin_bytes) - 1, 0) == -1.0
+
+
+def test_bench_reads_measured_traffic_of_every_kernel():
+    """bench.py's roofline.traffic comes from the newest committed `ncu --set full` raw page under profiles/: the page
+    must hold the five kernels of a frame-step under the names bench.py looks for (a renamed kernel would silently turn
+    traffic into null), and the dominant kernel's DRAM bytes must stay close to its algorithmic bytes."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    traffic, fname = bench.measured_traffic()
+    assert fname is not None, "no profiles/rNN_vMM_ncu_raw_B*.csv committed"
+    assert traffic is not None and set(traffic) == set(bench.KERNEL_PATTERNS), (fname, traffic)
+    for k, v in traffic.items():
+        assert 0 < v < 4 * bench.KERNEL_BYTES[k], (k, v, bench.KERNEL_BYTES[k])
+    assert traffic["pitch"] < 1.1 * bench.KERNEL_BYTES["pitch"]  # nothing re-read by the dominant kernel

@@ -222,6 +222,22 @@ def all_cpus():
         return list(range(os.cpu_count() or 1))
 
 
+def cgroup_cpu_quota():
+    """CPU-time quota of this container in cores (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited: with a quota
+    below the affinity count the all-core rate of the CPU arm is bounded by the quota, not by the thread count."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 def gpu_numa_cpus(torch, local):
     """CPUs of the NUMA node GPU `local` hangs off (sysfs), or None."""
     try:
@@ -255,9 +271,10 @@ def cpu_run(m, x_bt, threads):
     return x_bt.shape[0] * x_bt.shape[1] / r["seconds"], r["threads"]
 
 
-def cpu_side_measurements(m, x_bt, cores):
+def cpu_side_measurements(m, x_bt, cores, all_core_fps=None):
     """SURVEY 8(d) side figures of the CPU arm: one core, all-zero input (silent fast path), and the benches/sin.rs:9-20
-    shape (one second of a 440 Hz sine through a freshly constructed state, construction included)."""
+    shape (one second of a 440 Hz sine through a freshly constructed state, construction included); plus what bounds the
+    all-core rate on a shared box (container CPU quota, load average, measured all-core / one-core ratio)."""
     import oracle
     one = max(1, min(x_bt.shape[0], 8))
     fps1, _ = cpu_run(m, x_bt[:one], 1)
@@ -275,7 +292,9 @@ def cpu_side_measurements(m, x_bt, cores):
             lib.nno_process_frame(h, out.ctypes.data, sine[f].ctypes.data)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"one_core_frames_per_s": fps1, "silent_input_frames_per_s_all_cores": fps0,
+    return {"one_core_frames_per_s": fps1, "all_core_over_one_core": (all_core_fps / fps1) if all_core_fps else None, "cgroup_cpu_quota_cores": cgroup_cpu_quota(),
+            "load_avg_1min": os.getloadavg()[0],
+            "silent_input_frames_per_s_all_cores": fps0,
             "sin_1s_440hz_single_stream_ms": 1e3 * best,
             "sin_note": "benches/sin.rs:9-20 shape: 100 frames of a 440 Hz sine incl. state construction, one thread, best of 5"}
 
@@ -306,7 +325,7 @@ def run_reference(args):
         frames += n * T
     dt = time.perf_counter() - t0
     value = frames / dt
-    side = cpu_side_measurements(m, x, cores)
+    side = cpu_side_measurements(m, x, cores, value)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -556,7 +575,7 @@ def run_b200(args):
                "sample": "first %d streams x %d frames of the GPU workload, median of 3; oracle/nno_oracle.c (C restatement of the "
                          "reference; Rust toolchain absent), -O3 -march=native -ffp-contract=off, OpenMP one stream per thread, "
                          "OMP_PROC_BIND=%s OMP_PLACES=%s" % (n, T, os.environ.get("OMP_PROC_BIND"), os.environ.get("OMP_PLACES")),
-               **cpu_side_measurements(m, xs, cores)}
+               **cpu_side_measurements(m, xs, cores, fps)}
 
     if rank == 0:
         line = {

@@ -238,6 +238,17 @@ def cgroup_cpu_quota():
         return None
 
 
+def usable_threads(cpus):
+    """Threads the CPU arm runs: one per CPU of the affinity mask, capped by the container's CPU-time quota (on the GPU
+    boxes of this pool: 128 hardware threads visible, cpu.max = 16 cores -- 128 runnable threads only take turns being
+    throttled, and calling that "128 cores" would misstate the baseline)."""
+    q = cgroup_cpu_quota()
+    n = len(cpus)
+    if q is not None and q >= 1.0:
+        n = min(n, int(q))
+    return max(1, n)
+
+
 def gpu_numa_cpus(torch, local):
     """CPUs of the NUMA node GPU `local` hangs off (sysfs), or None."""
     try:
@@ -306,10 +317,10 @@ def run_reference(args):
     if rank != 0:
         return
     cpus = all_cpus()
-    cores = len(cpus)
+    cores = usable_threads(cpus)
     B, scaling, cfg = resolve_workload(args, world)
     T = args.frames
-    n = min(B, max(cores * 8, 8))
+    n = min(B, max(len(cpus) * 8, 8))
     from nnnoiseless_b200.synth import synth_streams  # numpy generator, same signal family as the GPU arm
     x = synth_streams(n, T, seed=1234).reshape(n, T, FRAME)  # n DISTINCT streams of the workload
     m = oracle_model(load_model_bytes(args.model) if args.model else None)
@@ -563,8 +574,8 @@ def run_b200(args):
             os.sched_setaffinity(0, cpus0)
         except (OSError, AttributeError):
             pass
-        cores = len(cpus0)
-        n = min(B, max(8, 16 * cores))
+        cores = usable_threads(cpus0)
+        n = min(B, max(8, 16 * len(cpus0)))
         xs = x[:, :n].permute(1, 0, 2).contiguous().cpu().numpy()  # [n][T][480]
         m = oracle_model(img)
         cpu_run(m, xs, cores)  # full-size warm-up (tables, page faults, thread pool)
